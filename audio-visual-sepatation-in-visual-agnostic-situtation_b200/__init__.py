@@ -1,0 +1,30 @@
+"""avsep_b200 -- B200-native (sm_100a) mix-and-separate spectrogram hot path.
+
+Drop-in for the hot path of abcqmars/audio-visual-sepatation-in-visual-agnostic-situtation:
+batched STFT (tcgen05 split-precision DFT GEMM), log-frequency warp + prepare derivations,
+synthesizer mask + sigmoid + weighted loss (forward / backward), un-warp + mask + iSTFT
+overlap-add.  Hand-written CUDA behind a C-ABI (include/avsep_b200.h); this package is the
+ctypes binding plus host-side mirrors of the reference's Python signatures.
+
+The directory name carries the upstream repo name (hyphens), so import it through the
+`avsep_b200` alias module at the repository root:  `import avsep_b200`.
+"""
+from . import _lib
+from ._lib import AvsepError, LIB_PATH
+from . import ops
+from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pit_lossmat, separate, stft,
+                  synth_masks, synth_masks_loss, synth_nosum, synth_pixelwise)
+from . import modules
+from .modules import BCELoss, BaseLoss, Bias, InnerProd, L1Loss, L2Loss, PitWrapper, activate
+from . import hotpath
+from .hotpath import (Step, _mix_n_and_stft, _stft, calc_metrics, istft_reconstruction, prepare, stft_batch, warp, warpgrid)
+from . import parallel
+
+__all__ = [
+    "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel",
+    "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
+    "stft", "istft", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
+    "_stft", "_mix_n_and_stft", "stft_batch", "Step",
+    "synth_masks", "synth_masks_loss", "synth_nosum", "synth_pixelwise", "list_loss", "pit_lossmat",
+    "InnerProd", "Bias", "BaseLoss", "BCELoss", "L1Loss", "L2Loss", "PitWrapper", "activate",
+]

@@ -1,0 +1,608 @@
+// STFT / iSTFT plan: split-precision DFT bases, TMA descriptors, bf16 staging kernels and the
+// C-ABI entry points avsep_stft / avsep_separate / avsep_istft.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "dft_gemm.cuh"
+#include "warp_taps.h"
+
+namespace avsep {
+
+// ---------------------------------------------------------------------------------------------
+// staging kernels
+// ---------------------------------------------------------------------------------------------
+// wave [S, L] fp32 -> reflect-padded (n_fft/2 each side, librosa center=True) bf16 hi/lo rows of
+// length Lpad.  Frame t of signal s is then the 1024-sample window starting at 256 t, which the
+// GEMM reads directly through an overlapping-row TMA descriptor (row stride 256 elements).
+__global__ void wave_split_kernel(const float* __restrict__ wave, int S, int L, int Lpad, size_t lo_stride,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int s = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Lpad) return;
+  int j = i - AVSEP_N_FFT / 2;
+  float x = 0.f;
+  if (i < L + AVSEP_N_FFT - 1 + 1) {            // positions beyond the padded signal stay zero
+    if (j < 0) j = -j;
+    if (j >= L) j = 2 * (L - 1) - j;
+    if (j >= 0 && j < L) x = wave[(size_t)s * L + j];
+  }
+  __nv_bfloat16 hi, lo;
+  split_bf16(x, hi, lo);
+  out[(size_t)s * Lpad + i] = hi;
+  out[lo_stride + (size_t)s * Lpad + i] = lo;
+}
+
+// Fallback when the overlapping-row descriptor is not available: materialise frames [S, T, 1024].
+__global__ void wave_frames_kernel(const float* __restrict__ wave, int S, int L, int T, size_t lo_stride,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int st = blockIdx.x;            // s * T + t
+  const int s = st / T, t = st % T;
+  for (int k = threadIdx.x; k < DFT_K; k += blockDim.x) {
+    int j = t * AVSEP_HOP + k - AVSEP_N_FFT / 2;
+    float x = 0.f;
+    if (k < AVSEP_N_FFT) {
+      if (j < 0) j = -j;
+      if (j >= L) j = 2 * (L - 1) - j;
+      if (j >= 0 && j < L) x = wave[(size_t)s * L + j];
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(x, hi, lo);
+    out[(size_t)st * DFT_K + k] = hi;
+    out[lo_stride + (size_t)st * DFT_K + k] = lo;
+  }
+}
+
+// K4 front half (main.py:213-246): un-warp each predicted mask to the linear frequency axis,
+// threshold, multiply the mixture spectrum and emit the inverse-DFT operand X[t, k] = (re | im),
+// time-major, as bf16 hi/lo.  One CTA = 64 bins x 32 frames of one mixture; the spectrum tile is
+// transposed through shared memory so both the [f][t] reads and the [t][f] writes are coalesced.
+struct SpecPrepParams {
+  const float* masks;   // [N, B, Hm, T]
+  const float* mag;     // [B, 512, T]
+  const float* phase;   // [B, 512, T] or null
+  const float* re;      // [B, 512, T] or null
+  const float* im;
+  int N, B, T, Hm;
+  int include_mix;
+  int binary;
+  float thres;
+  Taps ytap, xtap;      // un-warp taps (rows: 512 outputs over Hm inputs; cols: T over T)
+  int log_freq;
+  __nv_bfloat16* out;   // [2][S_cap][T][1024]
+  size_t lo_stride;
+};
+
+__global__ void __launch_bounds__(256) spec_prep_kernel(const SpecPrepParams p) {
+  __shared__ float tile[2][32][65];
+  const int b = blockIdx.z;
+  const int f0 = blockIdx.y * 64;
+  const int t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  const int t = t0 + tx;
+  const bool t_ok = t < p.T;
+  float bre[8], bim[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = f0 + ty + 8 * i;
+    bre[i] = 0.f;
+    bim[i] = 0.f;
+    if (t_ok) {
+      const size_t o = ((size_t)b * AVSEP_N_BINS + f) * p.T + t;
+      if (p.re) {
+        bre[i] = p.re[o];
+        bim[i] = p.im[o];
+      } else {
+        const float mg = p.mag[o];
+        float sn, cs;
+        sincosf(p.phase[o], &sn, &cs);
+        bre[i] = mg * cs;
+        bim[i] = mg * sn;
+      }
+    }
+  }
+  int x0 = 0;
+  float fx = 0.f;
+  if (t_ok && p.log_freq) {
+    x0 = p.xtap.i0[t];
+    fx = p.xtap.frac[t];
+  }
+  const int nsig = p.N + p.include_mix;
+  for (int j = 0; j < nsig; ++j) {
+    const int n = j - p.include_mix;   // -1 = mixture (mask 1)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int fl = ty + 8 * i;
+      float mk = 1.f;
+      if (n >= 0 && t_ok) {
+        const float* mp = p.masks + ((size_t)n * p.B + b) * (size_t)p.Hm * p.T;
+        if (p.log_freq) {
+          const int f = f0 + fl;
+          const int y0 = p.ytap.i0[f];
+          const float fy = p.ytap.frac[f];
+          float r0 = 0.f, r1 = 0.f;
+          const bool xa = x0 >= 0, xb = x0 + 1 < p.T;
+          if (y0 >= 0) {
+            const float* r = mp + (size_t)y0 * p.T;
+            r0 = (xa ? (1.f - fx) * __ldg(r + x0) : 0.f) + (xb ? fx * __ldg(r + x0 + 1) : 0.f);
+          }
+          if (y0 + 1 < p.Hm) {
+            const float* r = mp + (size_t)(y0 + 1) * p.T;
+            r1 = (xa ? (1.f - fx) * __ldg(r + x0) : 0.f) + (xb ? fx * __ldg(r + x0 + 1) : 0.f);
+          }
+          mk = (1.f - fy) * r0 + fy * r1;
+        } else {
+          mk = __ldg(mp + (size_t)(f0 + fl) * p.T + t);
+        }
+        if (p.binary) mk = mk > p.thres ? 1.f : 0.f;
+      }
+      tile[0][tx][fl] = bre[i] * mk;
+      tile[1][tx][fl] = bim[i] * mk;
+    }
+    __syncthreads();
+    // write 32 time rows x (64 re + 64 im) x (hi, lo): 16-byte chunks of 8 bf16
+    const size_t sig = (size_t)b * nsig + j;
+    for (int c = threadIdx.x; c < 32 * 2 * 8; c += 256) {
+      const int tr = c >> 4;           // time row in tile
+      const int part = (c >> 3) & 1;   // 0 re, 1 im
+      const int ch = c & 7;            // chunk of 8 bins
+      if (t0 + tr < p.T) {
+        __align__(16) __nv_bfloat16 hi[8];
+        __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(tile[part][tr][ch * 8 + e], hi[e], lo[e]);
+        const size_t o = (sig * p.T + (t0 + tr)) * DFT_K + part * AVSEP_N_BINS + f0 + ch * 8;
+        *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(p.out + p.lo_stride + o) = *reinterpret_cast<const uint4*>(lo);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace avsep
+
+struct avsep_plan {
+  int device = 0;
+  int max_signals = 0;
+  int wave_len = 0;
+  int T = 0;
+  int Lpad = 0;
+  int out_len = 0;
+  int kblock = 32;
+  bool overlap_tma = true;      // frames read through the overlapping-row descriptor
+  __nv_bfloat16* basis_fwd = nullptr;   // [2][1024][1024]  (hi rows 0..1023, lo rows 1024..2047)
+  __nv_bfloat16* basis_inv = nullptr;
+  __nv_bfloat16* wave_split = nullptr;  // [2][S_cap][Lpad]   (overlap) or [2][S_cap][T][1024] (frames)
+  __nv_bfloat16* spec_split = nullptr;  // [2][S_cap][T][1024], allocated on first inverse call
+  float* inv_env = nullptr;             // [256 * (T + 3)]
+  int* err_flag = nullptr;
+  CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave, tm_spec;
+  bool tm_spec_valid = false;
+  size_t workspace = 0;
+};
+
+namespace avsep {
+
+static int encode_map(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, int kblock) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(AVSEP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kblock == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(AVSEP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AVSEP_OK;
+}
+
+static int build_maps(avsep_plan* pl) {
+  const int bk = pl->kblock;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)DFT_K, (cuuint64_t)(2 * DFT_ROWS)};
+    cuuint64_t strides[1] = {(cuuint64_t)DFT_K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_M};
+    int rc = encode_map(&pl->tm_basis_fwd, pl->basis_fwd, 2, dims, strides, box, bk);
+    if (rc) return rc;
+    rc = encode_map(&pl->tm_basis_inv, pl->basis_inv, 2, dims, strides, box, bk);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_N, 1};
+    int rc = AVSEP_ERR_CUDA;
+    if (pl->overlap_tma) {
+      cuuint64_t strides[2] = {(cuuint64_t)AVSEP_HOP * 2, (cuuint64_t)pl->Lpad * 2};
+      rc = encode_map(&pl->tm_wave, pl->wave_split, 3, dims, strides, box, bk);
+      if (rc) pl->overlap_tma = false;   // driver rejected overlapping rows: materialise frames instead
+    }
+    if (!pl->overlap_tma) {
+      cuuint64_t strides[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
+      rc = encode_map(&pl->tm_wave, pl->wave_split, 3, dims, strides, box, bk);
+      if (rc) return rc;
+    }
+  }
+  if (pl->spec_split) {
+    cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
+    cuuint64_t strides[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_N, 1};
+    int rc = encode_map(&pl->tm_spec, pl->spec_split, 3, dims, strides, box, bk);
+    if (rc) return rc;
+    pl->tm_spec_valid = true;
+  }
+  return AVSEP_OK;
+}
+
+static void fill_basis(std::vector<uint16_t>& fwd, std::vector<uint16_t>& inv) {
+  const int NF = AVSEP_N_FFT;
+  std::vector<double> win(NF), cs(NF), sn(NF);
+  for (int n = 0; n < NF; ++n) {
+    win[n] = 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)NF);   // periodic Hann
+    cs[n] = std::cos(2.0 * M_PI * (double)n / (double)NF);
+    sn[n] = std::sin(2.0 * M_PI * (double)n / (double)NF);
+  }
+  fwd.assign((size_t)2 * DFT_ROWS * DFT_K, 0);
+  inv.assign((size_t)2 * DFT_ROWS * DFT_K, 0);
+  auto put = [](std::vector<uint16_t>& dst, int row, int k, double v) {
+    const float f = (float)v;
+    const uint16_t hi = host_f32_to_bf16(f);
+    const uint16_t lo = host_f32_to_bf16(f - host_bf16_to_f32(hi));
+    dst[(size_t)row * DFT_K + k] = hi;
+    dst[(size_t)(DFT_ROWS + row) * DFT_K + k] = lo;
+  };
+  // forward: row R = 128 m + 32 q + 16 part + i  <->  bin f = 64 m + 16 q + i, part 0 = cos, 1 = -sin
+  for (int R = 0; R < DFT_ROWS; ++R) {
+    const int m = R >> 7, q = (R >> 5) & 3, part = (R >> 4) & 1, i = R & 15;
+    const int f = 64 * m + 16 * q + i;
+    for (int n = 0; n < NF; ++n) {
+      const int a = (int)(((long long)f * n) % NF);
+      put(fwd, R, n, part == 0 ? win[n] * cs[a] : -win[n] * sn[a]);
+    }
+  }
+  // inverse: row R = 128 m + 32 q + jj  <->  sample n = 32 m + jj + 256 q of the frame;
+  // column k < 512: coefficient of Re X[k]; k >= 512: coefficient of Im X[k - 512]   (irfft, n = 1022)
+  for (int R = 0; R < DFT_ROWS; ++R) {
+    const int m = R >> 7, q = (R >> 5) & 3, jj = R & 31;
+    const int n = 32 * m + jj + 256 * q;
+    if (n >= NF) continue;
+    for (int f = 0; f < AVSEP_N_BINS; ++f) {
+      const double c = (f == 0 || f == NF / 2) ? 1.0 : 2.0;
+      const int a = (int)(((long long)f * n) % NF);
+      put(inv, R, f, win[n] * c * cs[a] / (double)NF);
+      put(inv, R, AVSEP_N_BINS + f, -win[n] * c * sn[a] / (double)NF);
+    }
+  }
+}
+
+template <int EPI>
+static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB, DftParams prm, cudaStream_t stream) {
+  const int grid = std::min(prm.total_tiles, sm_count());
+  if (grid <= 0) return AVSEP_OK;
+  if (pl->kblock == 64) {
+    auto kern = dft_gemm_kernel<64, EPI>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<64>::SMEM_BYTES));
+    kern<<<grid, DFT_THREADS, DftCfg<64>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  } else {
+    auto kern = dft_gemm_kernel<32, EPI>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<32>::SMEM_BYTES));
+    kern<<<grid, DFT_THREADS, DftCfg<32>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  }
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+static DftParams base_params(const avsep_plan* pl, int S) {
+  DftParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.num_signals = S;
+  prm.T = pl->T;
+  prm.n_tiles = ceil_div(pl->T, DFT_TILE_N);
+  prm.total_tiles = S * prm.n_tiles * DFT_M_TILES;
+  prm.lo_offset = pl->max_signals;
+  prm.out_len = pl->out_len;
+  prm.inv_env = pl->inv_env;
+  prm.err_flag = pl->err_flag;
+  return prm;
+}
+
+static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream) {
+  if (pl->overlap_tma) {
+    const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
+    dim3 grid(ceil_div(pl->Lpad, 256), S);
+    wave_split_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->Lpad, lo_stride, pl->wave_split);
+  } else {
+    const size_t lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
+    wave_frames_kernel<<<S * pl->T, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, lo_stride, pl->wave_split);
+  }
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+static int ensure_spec(avsep_plan* pl) {
+  if (pl->spec_split) return AVSEP_OK;
+  const size_t bytes = (size_t)2 * pl->max_signals * pl->T * DFT_K * sizeof(__nv_bfloat16);
+  AVSEP_CUDA(cudaMalloc(&pl->spec_split, bytes));
+  pl->workspace += bytes;
+  return build_maps(pl);
+}
+
+}  // namespace avsep
+
+using namespace avsep;
+
+extern "C" {
+
+int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
+  AVSEP_REQUIRE(plan != nullptr, "avsep_plan_create: plan is null");
+  *plan = nullptr;
+  AVSEP_REQUIRE(max_signals >= 1, "avsep_plan_create: max_signals must be >= 1 (got %d)", max_signals);
+  AVSEP_REQUIRE(wave_len > AVSEP_N_FFT / 2, "avsep_plan_create: wave_len %d too short for reflect padding of %d",
+                wave_len, AVSEP_N_FFT / 2);
+  int rc = require_sm100();
+  if (rc) return rc;
+  avsep_plan* pl = new avsep_plan();
+  cudaGetDevice(&pl->device);
+  pl->max_signals = max_signals;
+  pl->wave_len = wave_len;
+  pl->T = 1 + wave_len / AVSEP_HOP;
+  pl->Lpad = AVSEP_HOP * (pl->T + 4);
+  pl->out_len = AVSEP_HOP * (pl->T - 1);
+  const char* env_bk = getenv("AVSEP_DFT_KBLOCK");
+  pl->kblock = (env_bk && atoi(env_bk) == 64) ? 64 : 32;
+  const char* env_ov = getenv("AVSEP_DFT_NO_OVERLAP_TMA");
+  pl->overlap_tma = !(env_ov && atoi(env_ov) != 0);
+
+  std::vector<uint16_t> fwd, inv;
+  fill_basis(fwd, inv);
+  const size_t basis_bytes = fwd.size() * sizeof(uint16_t);
+  auto fail = [&](int code) { avsep_plan_destroy(pl); return code; };
+#define PLAN_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(set_error(AVSEP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)));   \
+  } while (0)
+  PLAN_CUDA(cudaMalloc(&pl->basis_fwd, basis_bytes));
+  PLAN_CUDA(cudaMalloc(&pl->basis_inv, basis_bytes));
+  PLAN_CUDA(cudaMemcpy(pl->basis_fwd, fwd.data(), basis_bytes, cudaMemcpyHostToDevice));
+  PLAN_CUDA(cudaMemcpy(pl->basis_inv, inv.data(), basis_bytes, cudaMemcpyHostToDevice));
+  pl->workspace += 2 * basis_bytes;
+
+  // reciprocal window sum-square envelope (librosa.filters.window_sumsquare), padded coordinates
+  {
+    const int n_env = AVSEP_HOP * (pl->T + 3);
+    std::vector<double> env(n_env, 0.0);
+    for (int t = 0; t < pl->T; ++t)
+      for (int n = 0; n < AVSEP_N_FFT; ++n) {
+        const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)AVSEP_N_FFT);
+        env[(size_t)t * AVSEP_HOP + n] += w * w;
+      }
+    std::vector<float> inv_env(n_env);
+    for (int i = 0; i < n_env; ++i) inv_env[i] = env[i] > 2.2250738585072014e-308 ? (float)(1.0 / env[i]) : 1.0f;
+    PLAN_CUDA(cudaMalloc(&pl->inv_env, sizeof(float) * n_env));
+    PLAN_CUDA(cudaMemcpy(pl->inv_env, inv_env.data(), sizeof(float) * n_env, cudaMemcpyHostToDevice));
+    pl->workspace += sizeof(float) * n_env;
+  }
+  PLAN_CUDA(cudaMalloc(&pl->err_flag, sizeof(int)));
+  PLAN_CUDA(cudaMemset(pl->err_flag, 0, sizeof(int)));
+
+  // staging buffer: large enough for either layout decision below
+  {
+    const size_t ov = (size_t)2 * max_signals * pl->Lpad;
+    const size_t fr = (size_t)2 * max_signals * pl->T * DFT_K;
+    const size_t elems = pl->overlap_tma ? ov : fr;
+    PLAN_CUDA(cudaMalloc(&pl->wave_split, elems * sizeof(__nv_bfloat16)));
+    pl->workspace += elems * sizeof(__nv_bfloat16);
+    const bool wanted_overlap = pl->overlap_tma;
+    rc = build_maps(pl);
+    if (rc) return fail(rc);
+    if (wanted_overlap && !pl->overlap_tma) {
+      // descriptor fell back to materialised frames: regrow the buffer and re-encode
+      cudaFree(pl->wave_split);
+      pl->workspace -= elems * sizeof(__nv_bfloat16);
+      PLAN_CUDA(cudaMalloc(&pl->wave_split, fr * sizeof(__nv_bfloat16)));
+      pl->workspace += fr * sizeof(__nv_bfloat16);
+      rc = build_maps(pl);
+      if (rc) return fail(rc);
+    }
+  }
+#undef PLAN_CUDA
+  *plan = pl;
+  return AVSEP_OK;
+}
+
+int avsep_plan_destroy(avsep_plan* pl) {
+  if (!pl) return AVSEP_OK;
+  cudaFree(pl->basis_fwd);
+  cudaFree(pl->basis_inv);
+  cudaFree(pl->wave_split);
+  cudaFree(pl->spec_split);
+  cudaFree(pl->inv_env);
+  cudaFree(pl->err_flag);
+  delete pl;
+  return AVSEP_OK;
+}
+
+int avsep_plan_frames(const avsep_plan* pl) { return pl ? pl->T : 0; }
+int avsep_plan_istft_len(const avsep_plan* pl) { return pl ? pl->out_len : 0; }
+size_t avsep_plan_workspace_bytes(const avsep_plan* pl) { return pl ? pl->workspace : 0; }
+
+int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_kblock: plan is null");
+  AVSEP_REQUIRE(kblock == 32 || kblock == 64, "avsep_plan_set_kblock: kblock must be 32 or 64 (got %d)", kblock);
+  AVSEP_CUDA(cudaDeviceSynchronize());
+  pl->kblock = kblock;
+  return build_maps(pl);
+}
+
+}  // extern "C"
+
+namespace avsep {
+int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
+              int reim_count, void* stream_) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_stft: plan is null");
+  AVSEP_REQUIRE(wave_dev && mag_dev, "avsep_stft: wave_dev and mag_dev are required");
+  AVSEP_REQUIRE((re_dev == nullptr) == (im_dev == nullptr), "avsep_stft: re_dev and im_dev must be given together");
+  AVSEP_REQUIRE(S >= 0 && S <= pl->max_signals, "avsep_stft: S = %d exceeds the plan capacity %d", S, pl->max_signals);
+  if (S == 0) return AVSEP_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = stage_waves(pl, wave_dev, S, stream);
+  if (rc) return rc;
+  DftParams prm = base_params(pl, S);
+  prm.mag = mag_dev;
+  prm.phase = phase_dev;
+  prm.re = re_dev;
+  prm.im = im_dev;
+  prm.reim_count = reim_count;
+  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, stream);
+}
+}  // namespace avsep
+
+extern "C" {
+
+int avsep_stft(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev,
+               float* im_dev, void* stream) {
+  return stft_impl(pl, wave_dev, S, mag_dev, phase_dev, re_dev, im_dev, S, stream);
+}
+
+int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const float* mag_dev, const float* phase_dev,
+                   const float* re_dev, const float* im_dev, int log_freq, int binary_mask, float mask_thres,
+                   int include_mix, float* wav_dev, void* stream_) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_separate: plan is null");
+  AVSEP_REQUIRE(N >= 0 && N <= 64 && B >= 0, "avsep_separate: bad N = %d / B = %d", N, B);
+  AVSEP_REQUIRE(N == 0 || masks_dev, "avsep_separate: masks_dev is null with N = %d", N);
+  AVSEP_REQUIRE(wav_dev != nullptr, "avsep_separate: wav_dev is null");
+  AVSEP_REQUIRE((re_dev && im_dev) || (mag_dev && phase_dev), "avsep_separate: give (mag, phase) or (re, im)");
+  AVSEP_REQUIRE(pl->T <= DFT_TILE_N, "avsep_separate: the fused overlap-add supports up to %d frames per clip (plan has %d)",
+                DFT_TILE_N, pl->T);
+  include_mix = include_mix ? 1 : 0;
+  const int nsig = N + include_mix;
+  AVSEP_REQUIRE((long long)B * nsig <= pl->max_signals, "avsep_separate: B * (N + mix) = %lld exceeds the plan capacity %d",
+                (long long)B * nsig, pl->max_signals);
+  if (B == 0 || nsig == 0) return AVSEP_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = ensure_spec(pl);
+  if (rc) return rc;
+  SpecPrepParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.masks = masks_dev;
+  sp.mag = mag_dev;
+  sp.phase = phase_dev;
+  sp.re = (re_dev && im_dev) ? re_dev : nullptr;
+  sp.im = (re_dev && im_dev) ? im_dev : nullptr;
+  sp.N = N;
+  sp.B = B;
+  sp.T = pl->T;
+  sp.Hm = log_freq ? 256 : AVSEP_N_BINS;
+  sp.include_mix = include_mix;
+  sp.binary = binary_mask;
+  sp.thres = mask_thres;
+  sp.log_freq = log_freq;
+  if (log_freq && N > 0) {
+    rc = get_taps(TAP_UNWARP_Y, 256, AVSEP_N_BINS, &sp.ytap);
+    if (rc) return rc;
+    rc = get_taps(TAP_LINEAR, pl->T, pl->T, &sp.xtap);
+    if (rc) return rc;
+  } else {
+    sp.log_freq = 0;
+    if (N > 0 && log_freq == 0) sp.Hm = AVSEP_N_BINS;
+  }
+  sp.out = pl->spec_split;
+  sp.lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
+  dim3 grid(ceil_div(pl->T, 32), AVSEP_N_BINS / 64, B);
+  spec_prep_kernel<<<grid, 256, 0, stream>>>(sp);
+  AVSEP_LAUNCH_CHECK();
+  DftParams prm = base_params(pl, B * nsig);
+  prm.wav = wav_dev;
+  return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, stream);
+}
+
+int avsep_istft(avsep_plan* pl, const float* mag_dev, const float* phase_dev, int S, float* wav_dev, void* stream) {
+  return avsep_separate(pl, nullptr, 0, S, mag_dev, phase_dev, nullptr, nullptr, 0, 0, 0.5f, 1, wav_dev, stream);
+}
+
+int avsep_debug_raw_gemm(avsep_plan* pl, int inverse, int S, float* out_dev, void* stream_) {
+  AVSEP_REQUIRE(pl && out_dev, "avsep_debug_raw_gemm: null argument");
+  AVSEP_REQUIRE(S >= 1 && S <= pl->max_signals, "avsep_debug_raw_gemm: bad S");
+  if (inverse) {
+    int rc = ensure_spec(pl);
+    if (rc) return rc;
+  }
+  DftParams prm = base_params(pl, S);
+  prm.raw = out_dev;
+  return launch_gemm<EPI_RAW>(pl, inverse ? pl->tm_basis_inv : pl->tm_basis_fwd, inverse ? pl->tm_spec : pl->tm_wave, prm,
+                              (cudaStream_t)stream_);
+}
+
+// product epilogues on the operands already staged in the plan (bench.py times the GEMM kernels alone with this)
+int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, void* stream_) {
+  AVSEP_REQUIRE(pl && out_dev, "avsep_debug_gemm_only: null argument");
+  AVSEP_REQUIRE(S >= 1 && S <= pl->max_signals, "avsep_debug_gemm_only: bad S");
+  DftParams prm = base_params(pl, S);
+  if (inverse) {
+    int rc = ensure_spec(pl);
+    if (rc) return rc;
+    AVSEP_REQUIRE(pl->T <= DFT_TILE_N, "avsep_debug_gemm_only: inverse needs T <= %d", DFT_TILE_N);
+    prm.wav = out_dev;
+    return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, (cudaStream_t)stream_);
+  }
+  prm.mag = out_dev;
+  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, (cudaStream_t)stream_);
+}
+
+int avsep_debug_basis(avsep_plan* pl, int inverse, float* out_host) {
+  AVSEP_REQUIRE(pl && out_host, "avsep_debug_basis: null argument");
+  std::vector<uint16_t> h((size_t)2 * DFT_ROWS * DFT_K);
+  AVSEP_CUDA(cudaMemcpy(h.data(), inverse ? pl->basis_inv : pl->basis_fwd, h.size() * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < (size_t)DFT_ROWS * DFT_K; ++i)
+    out_host[i] = host_bf16_to_f32(h[i]) + host_bf16_to_f32(h[(size_t)DFT_ROWS * DFT_K + i]);
+  return AVSEP_OK;
+}
+
+// staged operand of the forward GEMM (hi + lo) for signal s, as fp32 [T, 1024]: lets the tests
+// separate "staging is wrong" from "the tensor-core pipeline is wrong"
+int avsep_debug_staged_frames(avsep_plan* pl, int s, float* out_host) {
+  AVSEP_REQUIRE(pl && out_host && s >= 0 && s < pl->max_signals, "avsep_debug_staged_frames: bad argument");
+  AVSEP_CUDA(cudaDeviceSynchronize());
+  if (pl->overlap_tma) {
+    std::vector<uint16_t> hi(pl->Lpad), lo(pl->Lpad);
+    const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
+    AVSEP_CUDA(cudaMemcpy(hi.data(), pl->wave_split + (size_t)s * pl->Lpad, pl->Lpad * 2, cudaMemcpyDeviceToHost));
+    AVSEP_CUDA(cudaMemcpy(lo.data(), pl->wave_split + lo_stride + (size_t)s * pl->Lpad, pl->Lpad * 2, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < pl->T; ++t)
+      for (int k = 0; k < DFT_K; ++k)
+        out_host[(size_t)t * DFT_K + k] = host_bf16_to_f32(hi[t * AVSEP_HOP + k]) + host_bf16_to_f32(lo[t * AVSEP_HOP + k]);
+  } else {
+    const size_t n = (size_t)pl->T * DFT_K;
+    std::vector<uint16_t> hi(n), lo(n);
+    const size_t lo_stride = (size_t)pl->max_signals * n;
+    AVSEP_CUDA(cudaMemcpy(hi.data(), pl->wave_split + (size_t)s * n, n * 2, cudaMemcpyDeviceToHost));
+    AVSEP_CUDA(cudaMemcpy(lo.data(), pl->wave_split + lo_stride + (size_t)s * n, n * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) out_host[i] = host_bf16_to_f32(hi[i]) + host_bf16_to_f32(lo[i]);
+  }
+  return AVSEP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+// End-to-end steps of the hot path behind one C call (what bench.py times):
+//   train (config C2): STFT of the (N+1) signals -> prepare -> synth + sigmoid + weighted BCE -> backward
+//   eval  (config C1/C3): STFT -> prepare -> synth + sigmoid (+ loss) -> un-warp / threshold / mask -> iSTFT
+// Host-buffer variants add the H2D copy of the waveforms / K-vectors and the D2H copy of the result
+// inside the call.  feat_sound is the U-Net's output in the reference and never exists on the host
+// there, so it stays a device pointer.
+#include <vector>
+
+#include "common.cuh"
+
+struct avsep_plan;
+
+namespace avsep {
+int prepare_impl(const float* mag_mix, const float* const* mags, int N, int B, int T, int log_freq, int weighted,
+                 int binary, float* mix_w, float* const* mags_w, float* log_mix, float* weights, float* const* gt,
+                 cudaStream_t stream);
+int synth_forward_impl(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int N, int K, int HW,
+                       int act, float* out, int loss_kind, const float* gt, const float* weight, float* loss, void* scratch,
+                       cudaStream_t stream);
+int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
+              int reim_count, void* stream);
+int synth_backward_impl(const float* feat, const float* vecs, const float* scale, int B, int N, int K, int HW, int act,
+                        int loss_kind, const float* pred, const float* gt, const float* weight, const float* gscale,
+                        const float* dz, float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch,
+                        cudaStream_t stream);
+}  // namespace avsep
+
+struct avsep_step {
+  int B = 0, N = 0, K = 0, L = 0, T = 0, HW = 0, out_len = 0;
+  avsep_plan* plan = nullptr;
+  float* waves = nullptr;     // [N+1, B, L]  (index 0 = mixture)
+  float* vecs = nullptr;      // [B, N, K]
+  float* mag = nullptr;       // [(N+1) B, 512, T]
+  float* mix_re = nullptr;    // [B, 512, T]
+  float* mix_im = nullptr;
+  float* mix_w = nullptr;     // [B, 256, T]
+  float* log_mix = nullptr;
+  float* weights = nullptr;
+  float* mags_w = nullptr;    // [N, B, 256, T]
+  float* gt = nullptr;        // [N, B, 256, T]
+  float* pred = nullptr;      // [N, B, 256, T]
+  float* loss = nullptr;      // [1]
+  float* one = nullptr;       // [1] = 1.0f (upstream gradient of err.backward())
+  float* dvecs = nullptr;     // [B, N, K]
+  float* dscale = nullptr;    // [K]
+  float* dbias = nullptr;     // [1]
+  float* wav = nullptr;       // [B, N+1, out_len]
+  void* scratch = nullptr;
+};
+
+using namespace avsep;
+
+static int step_forward_common(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
+                               const float* scale_dev, const float* bias_dev, bool need_reim, cudaStream_t stream) {
+  const int B = st->B, N = st->N;
+  int rc = stft_impl(st->plan, waves_dev, (N + 1) * B, st->mag, nullptr, need_reim ? st->mix_re : nullptr,
+                     need_reim ? st->mix_im : nullptr, B, stream);
+  if (rc) return rc;
+  const size_t sig = (size_t)AVSEP_N_BINS * st->T;
+  const size_t img = (size_t)st->HW;
+  const float* mags[AVSEP_MAX_SRC];
+  float* mags_w[AVSEP_MAX_SRC];
+  float* gts[AVSEP_MAX_SRC];
+  for (int n = 0; n < N; ++n) {
+    mags[n] = st->mag + (size_t)(1 + n) * B * sig;
+    mags_w[n] = st->mags_w + (size_t)n * B * img;
+    gts[n] = st->gt + (size_t)n * B * img;
+  }
+  rc = prepare_impl(st->mag, mags, N, B, st->T, 1, 1, 1, st->mix_w, mags_w, st->log_mix, st->weights, gts, stream);
+  if (rc) return rc;
+  return synth_forward_impl(feat_dev, vecs_dev, scale_dev, bias_dev, B, N, st->K, st->HW, AVSEP_ACT_SIGMOID, st->pred,
+                            AVSEP_LOSS_BCE, st->gt, st->weights, st->loss, st->scratch, stream);
+}
+
+extern "C" {
+
+int avsep_step_destroy(avsep_step* st) {
+  if (!st) return AVSEP_OK;
+  avsep_plan_destroy(st->plan);
+  float* bufs[] = {st->waves, st->vecs, st->mag, st->mix_re, st->mix_im, st->mix_w, st->log_mix, st->weights, st->mags_w,
+                   st->gt, st->pred, st->loss, st->one, st->dvecs, st->dscale, st->dbias, st->wav};
+  for (float* b : bufs) cudaFree(b);
+  cudaFree(st->scratch);
+  delete st;
+  return AVSEP_OK;
+}
+
+int avsep_step_create(avsep_step** step, int B, int N, int K, int wave_len) {
+  AVSEP_REQUIRE(step != nullptr, "avsep_step_create: step is null");
+  *step = nullptr;
+  AVSEP_REQUIRE(B >= 1 && N >= 1 && N <= AVSEP_MAX_SRC && K >= 1 && K <= 256, "avsep_step_create: bad B=%d N=%d K=%d", B, N, K);
+  int rc = require_sm100();
+  if (rc) return rc;
+  avsep_step* st = new avsep_step();
+  st->B = B; st->N = N; st->K = K; st->L = wave_len;
+  rc = avsep_plan_create(&st->plan, (N + 1) * B, wave_len);
+  if (rc) { delete st; return rc; }
+  st->T = avsep_plan_frames(st->plan);
+  st->HW = 256 * st->T;
+  st->out_len = avsep_plan_istft_len(st->plan);
+  const size_t sig = (size_t)AVSEP_N_BINS * st->T, img = (size_t)st->HW;
+  struct { float** p; size_t n; } allocs[] = {
+      {&st->waves, (size_t)(N + 1) * B * wave_len}, {&st->vecs, (size_t)B * N * K}, {&st->mag, (size_t)(N + 1) * B * sig},
+      {&st->mix_re, (size_t)B * sig}, {&st->mix_im, (size_t)B * sig}, {&st->mix_w, (size_t)B * img},
+      {&st->log_mix, (size_t)B * img}, {&st->weights, (size_t)B * img}, {&st->mags_w, (size_t)N * B * img},
+      {&st->gt, (size_t)N * B * img}, {&st->pred, (size_t)N * B * img}, {&st->loss, 1}, {&st->one, 1},
+      {&st->dvecs, (size_t)B * N * K}, {&st->dscale, (size_t)K}, {&st->dbias, 1},
+      {&st->wav, (size_t)B * (N + 1) * st->out_len}};
+  for (auto& a : allocs) {
+    cudaError_t e = cudaMalloc(a.p, a.n * sizeof(float));
+    if (e != cudaSuccess) {
+      avsep_step_destroy(st);
+      return set_error(AVSEP_ERR_CUDA, "avsep_step_create: cudaMalloc of %zu bytes failed: %s", a.n * sizeof(float), cudaGetErrorString(e));
+    }
+  }
+  cudaError_t e = cudaMalloc(&st->scratch, avsep_synth_scratch_bytes(B, N, K, st->HW));
+  const float one = 1.0f;
+  if (e == cudaSuccess) e = cudaMemcpy(st->one, &one, sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    avsep_step_destroy(st);
+    return set_error(AVSEP_ERR_CUDA, "avsep_step_create: %s", cudaGetErrorString(e));
+  }
+  *step = st;
+  return AVSEP_OK;
+}
+
+int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
+                         const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
+                         float* dbias_dev, float* loss_dev, void* stream_) {
+  AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_train_dev: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, false, stream);
+  if (rc) return rc;
+  rc = synth_backward_impl(feat_dev, vecs_dev, scale_dev, st->B, st->N, st->K, st->HW, AVSEP_ACT_SIGMOID, AVSEP_LOSS_BCE,
+                           st->pred, st->gt, st->weights, st->one, nullptr, dfeat_dev, dvecs_dev ? dvecs_dev : st->dvecs,
+                           dscale_dev ? dscale_dev : st->dscale, dbias_dev ? dbias_dev : st->dbias, st->scratch, stream);
+  if (rc) return rc;
+  if (loss_dev) AVSEP_CUDA(cudaMemcpyAsync(loss_dev, st->loss, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  return AVSEP_OK;
+}
+
+int avsep_step_train_host(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
+                          const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_host, float* loss_host,
+                          void* stream_) {
+  AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev && loss_host, "avsep_step_train_host: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + 1) * st->B * st->L, cudaMemcpyHostToDevice, stream));
+  AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
+  int rc = avsep_step_train_dev(st, st->waves, st->vecs, feat_dev, scale_dev, bias_dev, dfeat_dev, nullptr, nullptr, nullptr,
+                                nullptr, stream);
+  if (rc) return rc;
+  AVSEP_CUDA(cudaMemcpyAsync(loss_host, st->loss, sizeof(float), cudaMemcpyDeviceToHost, stream));
+  if (dvecs_host)
+    AVSEP_CUDA(cudaMemcpyAsync(dvecs_host, st->dvecs, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyDeviceToHost, stream));
+  AVSEP_CUDA(cudaStreamSynchronize(stream));
+  return AVSEP_OK;
+}
+
+int avsep_step_eval_dev(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
+                        const float* scale_dev, const float* bias_dev, int binary_mask, float mask_thres, float* wav_dev,
+                        void* stream_) {
+  AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_eval_dev: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, true, stream);
+  if (rc) return rc;
+  return avsep_separate(st->plan, st->pred, st->N, st->B, nullptr, nullptr, st->mix_re, st->mix_im, 1, binary_mask, mask_thres, 1,
+                        wav_dev ? wav_dev : st->wav, stream);
+}
+
+int avsep_step_eval_host(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
+                         const float* scale_dev, const float* bias_dev, int binary_mask, float mask_thres, float* wav_host,
+                         void* stream_) {
+  AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev && wav_host, "avsep_step_eval_host: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + 1) * st->B * st->L, cudaMemcpyHostToDevice, stream));
+  AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
+  int rc = avsep_step_eval_dev(st, st->waves, st->vecs, feat_dev, scale_dev, bias_dev, binary_mask, mask_thres, st->wav, stream);
+  if (rc) return rc;
+  AVSEP_CUDA(cudaMemcpyAsync(wav_host, st->wav, sizeof(float) * (size_t)st->B * (st->N + 1) * st->out_len, cudaMemcpyDeviceToHost, stream));
+  AVSEP_CUDA(cudaStreamSynchronize(stream));
+  return AVSEP_OK;
+}
+
+avsep_plan* avsep_step_plan(avsep_step* st) { return st ? st->plan : nullptr; }
+
+const float* avsep_step_buffer(const avsep_step* st, int which) {
+  if (!st) return nullptr;
+  switch (which) {
+    case 0: return st->mag;
+    case 1: return st->mix_re;
+    case 2: return st->mix_im;
+    case 3: return st->mix_w;
+    case 4: return st->log_mix;
+    case 5: return st->weights;
+    case 6: return st->gt;
+    case 7: return st->pred;
+    case 8: return st->loss;
+    case 9: return st->dvecs;
+    case 10: return st->dscale;
+    case 11: return st->dbias;
+    case 12: return st->mags_w;
+    case 13: return st->wav;
+    default: return nullptr;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,498 @@
+// K3: the synthesizer mask -- InnerProd / Bias (models/synthesizer_net.py:6-70) for all N sources of
+// a mixture in one pass over feat_sound, fused with the caller's sigmoid (models/__init__.py:16-18)
+// and the list-form weighted loss (models/criterion.py:10-49), plus the backward pass.
+//
+// HBM-bound: feat_sound [B,K,HW] (8.4 MB per mixture at K=32, 256x256) is the dominant stream.  The
+// reference reads it once per source in the forward (cuBLAS M=1 batched GEMM) and materialises one
+// [B,K,H,W] outer product per source in the backward; here it is streamed exactly once per pass
+// with 128-bit loads, the K-vector of every source lives in shared memory, the per-channel
+// reductions for d(vec)/d(scale)/d(bias) use warp shuffles, and the loss is reduced in the same pass.
+#include "common.cuh"
+
+namespace avsep {
+
+constexpr int SYN_FWD_THREADS = 256;
+constexpr int SYN_BWD_THREADS = 128;
+constexpr int SYN_BWD_ITERS = 4;     // float4 groups per thread
+constexpr int SYN_KCHUNK = 32;       // channels per backward CTA (grid.z walks the chunks)
+constexpr int SYN_MAX_K = 256;
+
+__device__ __forceinline__ float act_apply(int act, float z) {
+  // torch.sigmoid in fp32: 1 / (1 + exp(-z)); saturates to exactly 0 / 1 like the reference
+  return act == AVSEP_ACT_SIGMOID ? 1.0f / (1.0f + expf(-z)) : z;
+}
+
+__device__ __forceinline__ float loss_elem(int kind, float p, float t) {
+  if (kind == AVSEP_LOSS_BCE) {
+    // F.binary_cross_entropy: -(t * max(log p, -100) + (1 - t) * max(log(1 - p), -100))
+    const float lp = fmaxf(logf(p), -100.f);
+    const float l1p = fmaxf(log1pf(-p), -100.f);
+    return (t - 1.f) * l1p - t * lp;
+  }
+  const float d = p - t;
+  return kind == AVSEP_LOSS_L1 ? fabsf(d) : d * d;
+}
+
+// d loss_elem / d pred (torch autograd semantics), without the 1/(numel*N) mean factor
+__device__ __forceinline__ float loss_grad(int kind, float p, float t) {
+  if (kind == AVSEP_LOSS_BCE) return (p - t) / fmaxf((1.f - p) * p, 1e-12f);   // ATen EPSILON = 1e-12
+  const float d = p - t;
+  if (kind == AVSEP_LOSS_L1) return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  return 2.f * d;
+}
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T r = 0;
+  if (warp == 0) {
+    r = lane < nwarps ? smem[lane] : (T)0;
+    r = warp_sum(r);
+  }
+  return r;   // valid in warp 0
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int NS, int VEC>
+__global__ void __launch_bounds__(SYN_FWD_THREADS)
+synth_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
+                 const float* __restrict__ bias, int B, int K, int HW, int act, float* __restrict__ out, int loss_kind,
+                 const float* __restrict__ gt, const float* __restrict__ weight, double* __restrict__ partial) {
+  __shared__ float vs[NS][SYN_MAX_K];
+  __shared__ double red[32];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < NS * K; i += blockDim.x) {
+    const int n = i / K, k = i % K;
+    vs[n][k] = vecs[((size_t)b * NS + n) * K + k] * (scale ? scale[k] : 1.f);
+  }
+  __syncthreads();
+  const float bz = bias ? bias[0] : 0.f;
+  const int px = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  double lsum = 0.0;
+  if (px < HW) {
+    float acc[NS][VEC];
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[n][e] = 0.f;
+    const float* fp = feat + (size_t)b * K * HW + px;
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+      float f[VEC];
+      if (VEC == 4) {
+        const float4 t4 = ld_stream(reinterpret_cast<const float4*>(fp + (size_t)k * HW));
+        f[0] = t4.x; f[1] = t4.y; f[2] = t4.z; f[3] = t4.w;
+      } else {
+        f[0] = __ldg(fp + (size_t)k * HW);
+      }
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
+        const float c = vs[n][k];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[n][e] = fmaf(c, f[e], acc[n][e]);
+      }
+    }
+    float w[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) w[e] = 1.f;
+    if (loss_kind != AVSEP_LOSS_NONE && weight) {
+      if (VEC == 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
+        w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+      } else {
+        w[0] = weight[(size_t)b * HW + px];
+      }
+    }
+    float ls = 0.f;
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      float pr[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) pr[e] = act_apply(act, acc[n][e] + bz);
+      const size_t o = ((size_t)n * B + b) * HW + px;
+      if (VEC == 4) *reinterpret_cast<float4*>(out + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+      else out[o] = pr[0];
+      if (loss_kind != AVSEP_LOSS_NONE) {
+        float t[VEC];
+        if (VEC == 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
+          t[0] = t4.x; t[1] = t4.y; t[2] = t4.z; t[3] = t4.w;
+        } else {
+          t[0] = gt[o];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) ls += w[e] * loss_elem(loss_kind, pr[e], t[e]);
+      }
+    }
+    lsum = (double)ls;
+  }
+  if (loss_kind != AVSEP_LOSS_NONE) {
+    const double tot = block_sum<double>(lsum, red);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+// deterministic final reduction of the per-CTA partial sums: loss = sum / (numel * N)
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(const double* __restrict__ partial, int n, double inv_count,
+                                                             float* __restrict__ loss) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  const double tot = block_sum<double>(s, red);
+  if (threadIdx.x == 0) loss[0] = (float)(tot * inv_count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// grid = (pixel chunks, B, K chunks of 32).  Each thread owns SYN_BWD_ITERS float4 pixel groups:
+//   dz[n]      = gscale * w * dl/dp * act'(p) / (numel * N)        (fused)   or given
+//   dfeat[k]   = sum_n dz[n] * vec[n][k] * scale[k]                streamed out
+//   S[n][k]   += dz[n] . feat[k]                                   registers -> warp shuffle -> CTA partial
+template <int NS, bool GIVEN>
+__global__ void __launch_bounds__(SYN_BWD_THREADS)
+synth_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale, int B,
+                 int K, int HW, int act, int loss_kind, const float* __restrict__ pred, const float* __restrict__ gt,
+                 const float* __restrict__ weight, const float* __restrict__ gscale, const float* __restrict__ dz_in,
+                 float inv_count, float* __restrict__ dfeat, float* __restrict__ s_partial /* [B][chunks][NS][Kp] */,
+                 float* __restrict__ dz_partial /* [B][chunks][NS] */, int Kp) {
+  __shared__ float vs[NS][SYN_KCHUNK];
+  __shared__ float red[SYN_BWD_THREADS / 32][NS * SYN_KCHUNK + NS];
+  const int b = blockIdx.y;
+  const int k0 = blockIdx.z * SYN_KCHUNK;
+  const int kn = min(SYN_KCHUNK, K - k0);
+  for (int i = threadIdx.x; i < NS * SYN_KCHUNK; i += blockDim.x) {
+    const int n = i / SYN_KCHUNK, k = i % SYN_KCHUNK;
+    vs[n][k] = (k < kn) ? vecs[((size_t)b * NS + n) * K + k0 + k] * (scale ? scale[k0 + k] : 1.f) : 0.f;
+  }
+  __syncthreads();
+  const float g = GIVEN ? 1.f : gscale[0] * inv_count;
+  float S[NS][SYN_KCHUNK];
+  float dzs[NS];
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    dzs[n] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k) S[n][k] = 0.f;
+  }
+  const int chunk_px = SYN_BWD_THREADS * 4 * SYN_BWD_ITERS;
+  const int base_px = blockIdx.x * chunk_px;
+#pragma unroll 1
+  for (int it = 0; it < SYN_BWD_ITERS; ++it) {
+    const int px = base_px + (it * SYN_BWD_THREADS + threadIdx.x) * 4;
+    if (px >= HW) break;
+    float dz[NS][4];
+    float w[4] = {1.f, 1.f, 1.f, 1.f};
+    if (!GIVEN && weight) {
+      const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
+      w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      const size_t o = ((size_t)n * B + b) * HW + px;
+      if (GIVEN) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dz_in + o);
+        dz[n][0] = d4.x; dz[n][1] = d4.y; dz[n][2] = d4.z; dz[n][3] = d4.w;
+      } else {
+        const float4 p4 = *reinterpret_cast<const float4*>(pred + o);
+        const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
+        const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+        const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float d = g * w[e] * loss_grad(loss_kind, pp[e], tt[e]);
+          if (act == AVSEP_ACT_SIGMOID) d *= (1.f - pp[e]) * pp[e];
+          dz[n][e] = d;
+        }
+      }
+      dzs[n] += (dz[n][0] + dz[n][1]) + (dz[n][2] + dz[n][3]);
+    }
+    const float* fp = feat + ((size_t)b * K + k0) * HW + px;
+    float* dp = dfeat ? dfeat + ((size_t)b * K + k0) * HW + px : nullptr;
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k) {
+      if (k < kn) {
+        const float4 f = ld_stream(reinterpret_cast<const float4*>(fp + (size_t)k * HW));
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const float c = vs[n][k];
+          o4.x = fmaf(c, dz[n][0], o4.x);
+          o4.y = fmaf(c, dz[n][1], o4.y);
+          o4.z = fmaf(c, dz[n][2], o4.z);
+          o4.w = fmaf(c, dz[n][3], o4.w);
+          S[n][k] += (dz[n][0] * f.x + dz[n][1] * f.y) + (dz[n][2] * f.z + dz[n][3] * f.w);
+        }
+        if (dp) st_stream(reinterpret_cast<float4*>(dp + (size_t)k * HW), o4);
+      }
+    }
+  }
+  // CTA reduction of S[n][k] and dzs[n]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k) {
+      const float r = warp_sum(S[n][k]);
+      if (lane == 0) red[warp][n * SYN_KCHUNK + k] = r;
+    }
+    const float r = warp_sum(dzs[n]);
+    if (lane == 0) red[warp][NS * SYN_KCHUNK + n] = r;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS * SYN_KCHUNK + NS; i += blockDim.x) {
+    float r = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < SYN_BWD_THREADS / 32; ++wq) r += red[wq][i];
+    const size_t cta = (size_t)b * gridDim.x + blockIdx.x;
+    if (i < NS * SYN_KCHUNK) {
+      const int n = i / SYN_KCHUNK, k = i % SYN_KCHUNK;
+      if (k < kn) s_partial[(cta * NS + n) * Kp + k0 + k] = r;
+    } else if (blockIdx.z == 0) {
+      dz_partial[cta * NS + (i - NS * SYN_KCHUNK)] = r;
+    }
+  }
+}
+
+// T[b][n][k] = sum_chunks S ; dvecs = scale * T ; tvec = T * vec (input of the dscale reduction)
+__global__ void synth_bwd_reduce_kernel(const float* __restrict__ s_partial, const float* __restrict__ vecs,
+                                        const float* __restrict__ scale, int B, int N, int K, int Kp, int chunks,
+                                        float* __restrict__ dvecs, float* __restrict__ tvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N * K) return;
+  const int k = i % K, n = (i / K) % N, b = i / (K * N);
+  float t = 0.f;
+  for (int c = 0; c < chunks; ++c) t += s_partial[(((size_t)b * chunks + c) * N + n) * Kp + k];
+  if (dvecs) dvecs[i] = t * (scale ? scale[k] : 1.f);
+  tvec[i] = t * vecs[i];
+}
+
+// block k < K: dscale[k] = sum_{b,n} tvec[b][n][k];  block K: dbias = sum dz_partial
+__global__ void __launch_bounds__(256) synth_bwd_final_kernel(const float* __restrict__ tvec, const float* __restrict__ dz_partial,
+                                                               int BN, int K, int n_dz, float* __restrict__ dscale,
+                                                               float* __restrict__ dbias) {
+  __shared__ double red[32];
+  double s = 0.0;
+  if ((int)blockIdx.x < K) {
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) s += (double)tvec[(size_t)i * K + blockIdx.x];
+    const double tot = block_sum<double>(s, red);
+    if (threadIdx.x == 0 && dscale) dscale[blockIdx.x] = (float)tot;
+  } else {
+    for (int i = threadIdx.x; i < n_dz; i += blockDim.x) s += (double)dz_partial[i];
+    const double tot = block_sum<double>(s, red);
+    if (threadIdx.x == 0 && dbias) dbias[0] = (float)tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward_nosum / forward_pixelwise (inference helpers, synthesizer_net.py:21-38)
+// ---------------------------------------------------------------------------------------------
+__global__ void synth_nosum_kernel(const float* __restrict__ feat, const float* __restrict__ vec, const float* __restrict__ scale,
+                                   const float* __restrict__ bias, int K, size_t HW, float* __restrict__ out) {
+  const int bk = blockIdx.y;   // b * K + k
+  const int k = bk % K;
+  const float c = vec[bk] * (scale ? scale[k] : 1.f);
+  const float bz = bias ? bias[0] : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x)
+    out[(size_t)bk * HW + i] = fmaf(c, feat[(size_t)bk * HW + i], bz);
+}
+
+__global__ void __launch_bounds__(256) synth_pixelwise_kernel(const float* __restrict__ feat, const float* __restrict__ fimg,
+                                                               const float* __restrict__ scale, const float* __restrict__ bias,
+                                                               int K, int P, int HW, float* __restrict__ out) {
+  // out[b][p][hw] = sum_k fimg[b][k][p] * scale[k] * feat[b][k][hw] + bias ; one CTA = (hw block, p, b)
+  extern __shared__ float vk[];
+  const int b = blockIdx.z, pidx = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) vk[k] = fimg[((size_t)b * K + k) * P + pidx] * (scale ? scale[k] : 1.f);
+  __syncthreads();
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= HW) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(vk[k], __ldg(feat + ((size_t)b * K + k) * HW + hw), acc);
+  out[((size_t)b * P + pidx) * HW + hw] = acc + (bias ? bias[0] : 0.f);
+}
+
+struct SynthScratch {
+  size_t loss_partial, s_partial, dz_partial, tvec, total;
+  int fwd_blocks_x, bwd_chunks, Kp;
+};
+
+SynthScratch synth_scratch_layout(int B, int N, int K, int HW) {
+  SynthScratch s;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  s.fwd_blocks_x = ceil_div(ceil_div(HW, 4), SYN_FWD_THREADS);
+  s.bwd_chunks = ceil_div(HW, SYN_BWD_THREADS * 4 * SYN_BWD_ITERS);
+  s.Kp = ceil_div(K, SYN_KCHUNK) * SYN_KCHUNK;
+  size_t off = 0;
+  s.loss_partial = off; off = up(off + sizeof(double) * (size_t)B * ceil_div(HW, SYN_FWD_THREADS));   // VEC=1 worst case
+  s.s_partial = off;    off = up(off + sizeof(float) * (size_t)B * s.bwd_chunks * N * s.Kp);
+  s.dz_partial = off;   off = up(off + sizeof(float) * (size_t)B * s.bwd_chunks * N);
+  s.tvec = off;         off = up(off + sizeof(float) * (size_t)B * N * K);
+  s.total = off;
+  return s;
+}
+
+template <int NS>
+static int synth_forward_n(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int K, int HW,
+                           int act, float* out, int loss_kind, const float* gt, const float* weight, float* loss,
+                           void* scratch, cudaStream_t stream) {
+  const bool vec4 = (HW % 4 == 0);
+  const SynthScratch lay = synth_scratch_layout(B, NS, K, HW);
+  double* partial = reinterpret_cast<double*>(static_cast<char*>(scratch) + lay.loss_partial);
+  const int bx = vec4 ? lay.fwd_blocks_x : ceil_div(HW, SYN_FWD_THREADS);
+  dim3 grid(bx, B);
+  if (vec4)
+    synth_fwd_kernel<NS, 4><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt,
+                                                                  weight, partial);
+  else
+    synth_fwd_kernel<NS, 1><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt,
+                                                                  weight, partial);
+  AVSEP_LAUNCH_CHECK();
+  if (loss_kind != AVSEP_LOSS_NONE) {
+    const double inv = 1.0 / ((double)B * (double)HW * (double)NS);
+    loss_finalize_kernel<<<1, 1024, 0, stream>>>(partial, bx * B, inv, loss);
+    AVSEP_LAUNCH_CHECK();
+  }
+  return AVSEP_OK;
+}
+
+template <int NS>
+static int synth_backward_n(const float* feat, const float* vecs, const float* scale, int B, int K, int HW, int act,
+                            int loss_kind, const float* pred, const float* gt, const float* weight, const float* gscale,
+                            const float* dz, float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch,
+                            cudaStream_t stream) {
+  const SynthScratch lay = synth_scratch_layout(B, NS, K, HW);
+  char* sc = static_cast<char*>(scratch);
+  float* s_partial = reinterpret_cast<float*>(sc + lay.s_partial);
+  float* dz_partial = reinterpret_cast<float*>(sc + lay.dz_partial);
+  float* tvec = reinterpret_cast<float*>(sc + lay.tvec);
+  dim3 grid(lay.bwd_chunks, B, lay.Kp / SYN_KCHUNK);
+  const float inv_count = (float)(1.0 / ((double)B * (double)HW * (double)NS));
+  if (dz)
+    synth_bwd_kernel<NS, true><<<grid, SYN_BWD_THREADS, 0, stream>>>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt,
+                                                                     weight, gscale, dz, inv_count, dfeat, s_partial,
+                                                                     dz_partial, lay.Kp);
+  else
+    synth_bwd_kernel<NS, false><<<grid, SYN_BWD_THREADS, 0, stream>>>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt,
+                                                                      weight, gscale, dz, inv_count, dfeat, s_partial,
+                                                                      dz_partial, lay.Kp);
+  AVSEP_LAUNCH_CHECK();
+  if (dvecs || dscale) {
+    const int n = B * NS * K;
+    synth_bwd_reduce_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(s_partial, vecs, scale, B, NS, K, lay.Kp, lay.bwd_chunks,
+                                                                  dvecs, tvec);
+    AVSEP_LAUNCH_CHECK();
+  }
+  if (dscale || dbias) {
+    synth_bwd_final_kernel<<<K + 1, 256, 0, stream>>>(tvec, dz_partial, B * NS, K, B * lay.bwd_chunks * NS, dscale, dbias);
+    AVSEP_LAUNCH_CHECK();
+  }
+  return AVSEP_OK;
+}
+
+int synth_forward_impl(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int N, int K, int HW,
+                       int act, float* out, int loss_kind, const float* gt, const float* weight, float* loss, void* scratch,
+                       cudaStream_t stream) {
+  switch (N) {
+    case 1: return synth_forward_n<1>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt, weight, loss, scratch, stream);
+    case 2: return synth_forward_n<2>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt, weight, loss, scratch, stream);
+    case 3: return synth_forward_n<3>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt, weight, loss, scratch, stream);
+    default: return synth_forward_n<4>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt, weight, loss, scratch, stream);
+  }
+}
+
+int synth_backward_impl(const float* feat, const float* vecs, const float* scale, int B, int N, int K, int HW, int act,
+                        int loss_kind, const float* pred, const float* gt, const float* weight, const float* gscale,
+                        const float* dz, float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch,
+                        cudaStream_t stream) {
+  switch (N) {
+    case 1: return synth_backward_n<1>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt, weight, gscale, dz, dfeat, dvecs, dscale, dbias, scratch, stream);
+    case 2: return synth_backward_n<2>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt, weight, gscale, dz, dfeat, dvecs, dscale, dbias, scratch, stream);
+    case 3: return synth_backward_n<3>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt, weight, gscale, dz, dfeat, dvecs, dscale, dbias, scratch, stream);
+    default: return synth_backward_n<4>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt, weight, gscale, dz, dfeat, dvecs, dscale, dbias, scratch, stream);
+  }
+}
+
+}  // namespace avsep
+
+using namespace avsep;
+
+extern "C" {
+
+size_t avsep_synth_scratch_bytes(int B, int N, int K, int HW) {
+  if (B < 1 || N < 1 || K < 1 || HW < 1) return 256;
+  return synth_scratch_layout(B, N, K, HW).total;
+}
+
+int avsep_synth_forward(const float* feat_dev, const float* vecs_dev, const float* scale_dev, const float* bias_dev, int B,
+                        int N, int K, int HW, int activation, float* out_dev, int loss_kind, const float* gt_dev,
+                        const float* weight_dev, float* loss_dev, void* scratch_dev, void* stream) {
+  AVSEP_REQUIRE(feat_dev && vecs_dev && out_dev, "avsep_synth_forward: feat/vecs/out must be non-null");
+  AVSEP_REQUIRE(N >= 1 && N <= AVSEP_MAX_SRC, "avsep_synth_forward: N = %d outside [1, %d]", N, AVSEP_MAX_SRC);
+  AVSEP_REQUIRE(K >= 1 && K <= SYN_MAX_K, "avsep_synth_forward: K = %d outside [1, %d]", K, SYN_MAX_K);
+  AVSEP_REQUIRE(B >= 0 && B <= 65535 && HW >= 1, "avsep_synth_forward: bad B = %d / HW = %d", B, HW);
+  AVSEP_REQUIRE(activation == AVSEP_ACT_NONE || activation == AVSEP_ACT_SIGMOID, "avsep_synth_forward: unknown activation %d", activation);
+  AVSEP_REQUIRE(loss_kind >= AVSEP_LOSS_NONE && loss_kind <= AVSEP_LOSS_BCE, "avsep_synth_forward: unknown loss kind %d", loss_kind);
+  if (loss_kind != AVSEP_LOSS_NONE)
+    AVSEP_REQUIRE(gt_dev && loss_dev && scratch_dev, "avsep_synth_forward: the fused loss needs gt_dev, loss_dev and scratch_dev");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  return synth_forward_impl(feat_dev, vecs_dev, scale_dev, bias_dev, B, N, K, HW, activation, out_dev, loss_kind, gt_dev,
+                            weight_dev, loss_dev, scratch_dev, (cudaStream_t)stream);
+}
+
+int avsep_synth_backward(const float* feat_dev, const float* vecs_dev, const float* scale_dev, int B, int N, int K, int HW,
+                         int activation, int loss_kind, const float* pred_dev, const float* gt_dev, const float* weight_dev,
+                         const float* gscale_dev, const float* dz_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
+                         float* dbias_dev, void* scratch_dev, void* stream) {
+  AVSEP_REQUIRE(feat_dev && vecs_dev && scratch_dev, "avsep_synth_backward: feat/vecs/scratch must be non-null");
+  AVSEP_REQUIRE(N >= 1 && N <= AVSEP_MAX_SRC, "avsep_synth_backward: N = %d outside [1, %d]", N, AVSEP_MAX_SRC);
+  AVSEP_REQUIRE(K >= 1 && K <= SYN_MAX_K, "avsep_synth_backward: K = %d outside [1, %d]", K, SYN_MAX_K);
+  AVSEP_REQUIRE(B >= 0 && B <= 65535 && HW >= 4 && HW % 4 == 0, "avsep_synth_backward: bad B = %d / HW = %d (HW must be a multiple of 4)", B, HW);
+  if (!dz_dev) {
+    AVSEP_REQUIRE(pred_dev && gt_dev && gscale_dev, "avsep_synth_backward: fused mode needs pred_dev, gt_dev and gscale_dev");
+    AVSEP_REQUIRE(loss_kind >= AVSEP_LOSS_L1 && loss_kind <= AVSEP_LOSS_BCE, "avsep_synth_backward: unknown loss kind %d", loss_kind);
+  }
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  return synth_backward_impl(feat_dev, vecs_dev, scale_dev, B, N, K, HW, activation, loss_kind, pred_dev, gt_dev, weight_dev,
+                             gscale_dev, dz_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, scratch_dev, (cudaStream_t)stream);
+}
+
+int avsep_synth_nosum(const float* feat_dev, const float* vec_dev, const float* scale_dev, const float* bias_dev, int B, int K,
+                      int HW, float* out_dev, void* stream) {
+  AVSEP_REQUIRE(feat_dev && vec_dev && out_dev, "avsep_synth_nosum: null tensor");
+  AVSEP_REQUIRE(B >= 0 && K >= 1 && HW >= 1 && (long long)B * K <= 65535, "avsep_synth_nosum: bad shape");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  dim3 grid(std::min(ceil_div(HW, 256), 1024), B * K);
+  synth_nosum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat_dev, vec_dev, scale_dev, bias_dev, K, (size_t)HW, out_dev);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+int avsep_synth_pixelwise(const float* feat_dev, const float* feats_img_dev, const float* scale_dev, const float* bias_dev, int B,
+                          int K, int P, int HW, float* out_dev, void* stream) {
+  AVSEP_REQUIRE(feat_dev && feats_img_dev && out_dev, "avsep_synth_pixelwise: null tensor");
+  AVSEP_REQUIRE(B >= 0 && B <= 65535 && K >= 1 && K <= 4096 && P >= 1 && P <= 65535 && HW >= 1, "avsep_synth_pixelwise: bad shape");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  dim3 grid(ceil_div(HW, 256), P, B);
+  synth_pixelwise_kernel<<<grid, 256, K * sizeof(float), (cudaStream_t)stream>>>(feat_dev, feats_img_dev, scale_dev, bias_dev, K,
+                                                                                 P, HW, out_dev);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's functions on the hot path (same names, argument meaning and
+error behaviour), so main.py / SoP++/main.py / inference.py / dataset/base.py can switch to the
+B200 path by changing imports only.  See INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import check, lib
+
+
+# ------------------------------------------------------------------------------------------------
+# utils.py
+# ------------------------------------------------------------------------------------------------
+def warpgrid(bs, HO, WO, warp=True):
+    """utils.warpgrid (utils.py:12-26), kept for call-site compatibility only.
+
+    The B200 path never materialises this grid: `warp()` below applies the same resample from two
+    tap tables.  Code that still calls F.grid_sample(x, warpgrid(...)) gets the identical grid.
+    """
+    x = np.linspace(-1, 1, WO)
+    y = np.linspace(-1, 1, HO)
+    xv, yv = np.meshgrid(x, y)
+    grid = np.zeros((bs, HO, WO, 2))
+    grid_x = xv
+    if warp:
+        grid_y = (np.power(21, (yv + 1) / 2) - 11) / 10
+    else:
+        grid_y = np.log(yv * 10 + 11) / np.log(21) * 2 - 1
+    grid[:, :, :, 0] = grid_x
+    grid[:, :, :, 1] = grid_y
+    return grid.astype(np.float32)
+
+
+def warp(x, HO, warp=True):
+    """Replaces `F.grid_sample(x, torch.from_numpy(warpgrid(B, HO, T, warp)).to(device), align_corners=False)`
+    (main.py:62-66, 216-220; inference.py:47-49, 458-462; SoP++/main.py:57-61, 283-285)."""
+    return ops.warp(x, HO, warp)
+
+
+def istft_reconstruction(mag, phase, hop_length=256):
+    """utils.istft_reconstruction (utils.py:101-104): numpy [512,T] x2 -> numpy float64 [256 (T-1)] in [-1, 1]."""
+    if hop_length != ops.HOP:
+        raise _lib.AvsepError(f"istft_reconstruction: only hop_length={ops.HOP} is supported, got {hop_length}")
+    m = torch.as_tensor(np.ascontiguousarray(mag), dtype=torch.float32).cuda(non_blocking=True)
+    p = torch.as_tensor(np.ascontiguousarray(phase), dtype=torch.float32).cuda(non_blocking=True)
+    wav = ops.istft(m[None], p[None])[0]
+    return wav.double().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# dataset/base.py
+# ------------------------------------------------------------------------------------------------
+def _stft(audio, stft_frame=1022, stft_hop=256, device="cuda"):
+    """BaseDataset._stft (dataset/base.py:142-147): numpy float32 [L] -> (amp, phase) torch [512, T].
+
+    Runs on the GPU; call it from the main process on collated waveforms, not from forked
+    DataLoader workers (SURVEY.md section 8(b) threading)."""
+    if stft_frame != ops.N_FFT or stft_hop != ops.HOP:
+        raise _lib.AvsepError(f"_stft: only n_fft={ops.N_FFT}, hop={ops.HOP} are supported")
+    w = torch.as_tensor(np.ascontiguousarray(audio), dtype=torch.float32).to(device, non_blocking=True)
+    amp, phase = ops.stft(w)
+    return amp, phase
+
+
+def _mix_n_and_stft(audios, audio_mix, device="cuda"):
+    """BaseDataset._mix_n_and_stft (dataset/base.py:174-189): one batched STFT for the mix and the N sources.
+
+    audios: list of N numpy [L]; audio_mix numpy [L] -> (amp_mix [1,512,T], mags list of [1,512,T], phase_mix [1,512,T]);
+    like the reference, `audios` entries are replaced by torch tensors."""
+    N = len(audios)
+    stack = np.stack([np.asarray(audio_mix, dtype=np.float32)] + [np.asarray(a, dtype=np.float32) for a in audios])
+    w = torch.from_numpy(stack).to(device, non_blocking=True)
+    mag, _, re, im = ops.stft(w, phase=False, complex_parts=True)
+    phase_mix = torch.atan2(im[0], re[0])
+    for n in range(N):
+        audios[n] = torch.from_numpy(np.asarray(audios[n]))
+    return mag[0].unsqueeze(0), [mag[1 + n].unsqueeze(0) for n in range(N)], phase_mix.unsqueeze(0)
+
+
+def stft_batch(audios: torch.Tensor, audio_mix: Optional[torch.Tensor] = None):
+    """Batched form for the collated batch: audios [N,B,L] (+ audio_mix [B,L],
+    default sum over sources, dataset/music.py:127) -> dict(mag_mix [B,1,512,T], mags list, phase_mix)."""
+    N, B, L = audios.shape
+    mix = audios.sum(dim=0) if audio_mix is None else audio_mix
+    w = torch.cat([mix[None], audios], dim=0).reshape((N + 1) * B, L)
+    mag, phase = ops.stft(w, phase=True)
+    mag = mag.view(N + 1, B, 1, ops.N_BINS, -1)
+    phase = phase.view(N + 1, B, 1, ops.N_BINS, -1)
+    return dict(mag_mix=mag[0], mags=[mag[1 + n] for n in range(N)], phase_mix=phase[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# main.py
+# ------------------------------------------------------------------------------------------------
+def prepare(batch_data, args, use_vis=False, is_share=False, load_clips=False):
+    """NetWrapper.prepare (main.py:51-95) with the same return tuples; like the reference it rebinds
+    batch_data['mags'][n] to the warped magnitudes (main.py:66)."""
+    mag_mix = batch_data['mag_mix']
+    mags = batch_data['mags']
+    N = args.num_mix
+    mags_w, mix_w, log_mix, gt_masks, weights = ops.prepare(
+        mag_mix, [mags[n] for n in range(N)], log_freq=bool(args.log_freq),
+        weighted_loss=bool(args.weighted_loss), binary_mask=bool(args.binary_mask))
+    for n in range(N):
+        mags[n] = mags_w[n]
+    if use_vis or getattr(args, "fusion_type", None) == "share" or is_share:
+        frames = batch_data['frames']
+        clips = batch_data['clips'] if load_clips else None
+        return frames, clips, mags, mix_w, log_mix, gt_masks, weights
+    return mags, mix_w, log_mix, gt_masks, weights
+
+
+class _Meter:
+    """utils.AverageMeter (utils.py:39-78), unweighted."""
+
+    def __init__(self):
+        self.sum, self.count = 0.0, 0
+
+    def update(self, val):
+        self.sum += float(val)
+        self.count += 1
+
+    def average(self):
+        return self.sum / self.count if self.count else 0.0
+
+
+def calc_metrics(batch_data, outputs, args, get_metrics: Optional[Callable] = None, rng: Optional[np.random.Generator] = None):
+    """calc_metrics (main.py:197-286): un-warp, threshold, mask, iSTFT on the GPU in one call for the
+    whole batch, then the per-clip metric call.  `get_metrics` defaults to asteroid's (as the reference
+    imports it, main.py:25); pass any callable with the same signature.  Returns the reference's list
+    [0, sdr, sir, sar, sdr_ls, sir_ls, si_sdr_ls, si_sdr].  `rng` seeds the all-zero-prediction guard
+    (main.py:248-249 uses the unseeded global numpy RNG)."""
+    if get_metrics is None:
+        try:
+            from asteroid.metrics import get_metrics as _gm   # noqa: the reference's own dependency
+        except Exception as e:                                 # pragma: no cover
+            raise _lib.AvsepError("calc_metrics: asteroid is not installed; pass get_metrics=...") from e
+        get_metrics = _gm
+    mag_mix = batch_data['mag_mix']
+    phase_mix = batch_data['phase_mix']
+    audios = batch_data['audios']
+    pred_masks_ = outputs['pred_masks']
+    N = args.num_mix
+    B = mag_mix.size(0)
+    dev = pred_masks_[0].device
+    wav = ops.separate([pred_masks_[n] for n in range(N)], mag_mix.to(dev, non_blocking=True),
+                       phase_mix.to(dev, non_blocking=True), log_freq=bool(args.log_freq),
+                       binary_mask=bool(args.binary_mask), mask_thres=float(args.mask_thres), include_mix=True)
+    wav = wav.double().cpu().numpy()                     # one D2H of [B, N+1, L] instead of N mask tensors
+    sdr_m, sir_m, sar_m, sisdr_m = _Meter(), _Meter(), _Meter(), _Meter()
+    sdr_ls, sir_ls, si_sdr_ls = [], [], []
+    for j in range(B):
+        mix_wav = wav[j, 0]
+        preds_wav = [wav[j, 1 + n] for n in range(N)]
+        for n in range(N):
+            if np.all(preds_wav[n] == 0):
+                r = rng.random(preds_wav[n].shape) if rng is not None else np.random.rand(*preds_wav[n].shape)
+                preds_wav[n] = 0.01 * r
+        L = preds_wav[0].shape[0]
+        gts_wav = [np.asarray(audios[n][j, 0:L].cpu().numpy() if torch.is_tensor(audios[n]) else audios[n][j, 0:L])
+                   for n in range(N)]
+        md = get_metrics(mix_wav[0:L], np.asarray(gts_wav), np.asarray(preds_wav), sample_rate=11025,
+                         metrics_list=['sdr', 'sir', 'sar', 'si_sdr'])
+        sdr_m.update(md['sdr']); sir_m.update(md['sir']); sar_m.update(md['sar']); sisdr_m.update(md['si_sdr'])
+        sdr_ls.append(md['sdr']); sir_ls.append(md['sir']); si_sdr_ls.append(md['si_sdr'])
+    return [0, sdr_m.average(), sir_m.average(), sar_m.average(), sdr_ls, sir_ls, si_sdr_ls, sisdr_m.average()]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused end-to-end steps (what bench.py measures)
+# ------------------------------------------------------------------------------------------------
+class _DevView:
+    """Borrowed fp32 device memory exposed through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr="<f4", data=(ptr, False), version=2)
+
+
+class Step:
+    """avsep_step: the whole hot path of one batch behind one C call (see include/avsep_b200.h)."""
+
+    BUFFERS = dict(mag=0, mix_re=1, mix_im=2, mag_mix_w=3, log_mag_mix=4, weights=5, gt_masks=6, pred_masks=7,
+                   loss=8, dvecs=9, dscale=10, dbias=11, mags_w=12, wav=13)
+
+    def __init__(self, B: int, N: int, K: int = 32, wave_len: int = 65535):
+        h = C.c_void_p()
+        check(lib.avsep_step_create(C.byref(h), B, N, K, wave_len), "avsep_step_create")
+        self._h = h
+        self.B, self.N, self.K, self.L = B, N, K, wave_len
+        self.T = 1 + wave_len // ops.HOP
+        self.out_len = ops.HOP * (self.T - 1)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            torch.cuda.synchronize()
+            lib.avsep_step_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape(self, name):
+        B, N, K, T = self.B, self.N, self.K, self.T
+        return dict(mag=((N + 1) * B, 512, T), mix_re=(B, 512, T), mix_im=(B, 512, T), mag_mix_w=(B, 1, 256, T),
+                    log_mag_mix=(B, 1, 256, T), weights=(B, 1, 256, T), gt_masks=(N, B, 1, 256, T),
+                    pred_masks=(N, B, 1, 256, T), loss=(1,), dvecs=(B, N, K), dscale=(K,), dbias=(1,),
+                    mags_w=(N, B, 1, 256, T), wav=(B, N + 1, self.out_len))[name]
+
+    def buffer(self, name: str) -> torch.Tensor:
+        """Copy of one of the step's device intermediates (tests / debugging)."""
+        shape = self._shape(name)
+        ptr = lib.avsep_step_buffer(self._h, self.BUFFERS[name])
+        if not ptr:
+            raise _lib.AvsepError(f"Step.buffer: no buffer named {name}")
+        return torch.as_tensor(_DevView(int(ptr), shape), device="cuda").clone()
+
+    # waves: [N+1, B, L] (index 0 = mixture); vecs [B,N,K]; feat [B,K,256,T] (device)
+    def train_dev(self, waves, vecs, feat, scale, bias, dfeat, dvecs=None, dscale=None, dbias=None, loss=None):
+        check(lib.avsep_step_train_dev(self._h, waves.data_ptr(), vecs.data_ptr(), feat.data_ptr(), ops._p(scale), ops._p(bias),
+                                       ops._p(dfeat), ops._p(dvecs), ops._p(dscale), ops._p(dbias), ops._p(loss), ops._stream()),
+              "avsep_step_train_dev")
+
+    def train_host(self, waves_host, vecs_host, feat, scale, bias, dfeat, dvecs_host=None):
+        """Host buffers in (pinned CPU tensors), loss out as a python float; H2D / D2H inside the call."""
+        loss = np.zeros(1, dtype=np.float32)
+        check(lib.avsep_step_train_host(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
+                                        ops._p(bias), ops._p(dfeat), ops._p(dvecs_host), loss.ctypes.data, ops._stream()),
+              "avsep_step_train_host")
+        return float(loss[0])
+
+    def eval_dev(self, waves, vecs, feat, scale, bias, wav=None, binary_mask=True, mask_thres=0.5):
+        check(lib.avsep_step_eval_dev(self._h, waves.data_ptr(), vecs.data_ptr(), feat.data_ptr(), ops._p(scale), ops._p(bias),
+                                      int(binary_mask), float(mask_thres), ops._p(wav), ops._stream()), "avsep_step_eval_dev")
+
+    def eval_host(self, waves_host, vecs_host, feat, scale, bias, wav_host, binary_mask=True, mask_thres=0.5):
+        check(lib.avsep_step_eval_host(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
+                                       ops._p(bias), int(binary_mask), float(mask_thres), wav_host.data_ptr(), ops._stream()),
+              "avsep_step_eval_host")
+        return wav_host

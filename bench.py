@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the mix-and-separate spectrogram hot path (BASELINE.json: separated mixtures/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|eval]
+
+Workload (config C2, BASELINE.json configs[1]): MUSIC N=2 training step, batch 80 per GPU:
+STFT of the (N+1) signals of every mixture (65535 samples @ 11025 Hz, n_fft 1022 / hop 256) ->
+prepare (log-frequency warp 512->256, weights, ground-truth masks, log magnitude) -> K=32
+synthesizer masks + sigmoid + weighted BCE -> full backward (dfeat_sound, dvecs, dscale, dbias).
+Synthetic MUSIC-shaped inputs (harmonic tones); feat_sound ~ N(0,1) stands in
+for the U-Net output and is device-resident, exactly as in the reference.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput, `e2e` = the same step through
+the host-buffer C-ABI entry point (pinned waveforms + K-vectors H2D, loss D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L = 65535
+N_SRC = 2
+K_CH = 32
+B_PER_GPU = 80
+T = 256
+HW = 256 * 256
+METRIC = "separated mixtures/sec"
+UNIT = "mixtures/s"
+
+# algorithmic bytes / flops per mixture at N=2 (each boundary tensor touched once)
+ALG = {
+    "dft_gemm_fwd": dict(bound="tensor", flops=1.607e9),                       # 3 signals x 0.536 GFLOP
+    "wave_split": dict(bound="hbm", bytes=786420 + 3 * 66560 * 4),             # fp32 in + bf16 hi/lo out
+    "prepare": dict(bound="hbm", bytes=1572864 + 786432 + 1048576),            # warp in + out + derived out
+    "synth_fwd_loss": dict(bound="hbm", bytes=8388864 + 524288 + 1310720),     # synth in/out + loss in
+    "synth_bwd": dict(bound="hbm", bytes=9699328 + 8388608),                   # bwd in + out
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tensor=float(p["bf16_tflops"]),
+                    tensor_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+def make_waves(B, N, seed):
+    """Harmonic-tone sources [N+1, B, L] (index 0 = mixture = sum of sources / already divided by N)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(L, dtype=torch.float64) / 11025.0
+    f0 = torch.exp(torch.empty(B, N, dtype=torch.float64).uniform_(np.log(110.0), np.log(880.0), generator=g))
+    sig = torch.zeros(B, N, L, dtype=torch.float64)
+    for h in range(1, 9):
+        ph = torch.empty(B, N, 1, dtype=torch.float64).uniform_(0, 2 * np.pi, generator=g)
+        sig += (1.0 / h) * torch.sin(2 * np.pi * h * f0[..., None] * t + ph)
+    am = torch.empty(B, N, 1, dtype=torch.float64).uniform_(0.2, 2.0, generator=g)
+    sig *= 0.5 + 0.5 * torch.sin(2 * np.pi * am * t)
+    sig += 0.01 * torch.randn(B, N, L, dtype=torch.float64, generator=g)
+    peak = torch.empty(B, N, 1, dtype=torch.float64).uniform_(0.5, 1.0, generator=g)
+    sig *= peak / sig.abs().amax(dim=-1, keepdim=True)
+    sig = (sig.clamp_(-1, 1) / N).float()
+    src = sig.permute(1, 0, 2).contiguous()                       # [N, B, L]
+    mix = src.sum(dim=0, keepdim=True)
+    return torch.cat([mix, src], dim=0).contiguous()              # [N+1, B, L]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")})
+            if sm:
+                out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(rows[0][2]), reasons=reasons, samples=len(sm),
+                           power_w_max=max(float(r[3]) for r in rows))
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def time_calls(fn, iters, warmup=2):
+    """Average device time (ms) of fn() over `iters` calls, CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the reference's own torch path on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(B, seed):
+    from oracle import torch_ref_path as TP
+    waves = make_waves(B, N_SRC, seed)                            # [N+1, B, L]
+    waves_bsl = waves.permute(1, 0, 2).contiguous()               # [B, N+1, L]
+    g = torch.Generator().manual_seed(seed + 1)
+    feat = torch.randn(B, K_CH, 256, 256, generator=g)
+    vecs = torch.sigmoid(torch.randn(B, N_SRC, K_CH, generator=g))
+    scale = torch.ones(K_CH, requires_grad=True)
+    bias = torch.zeros(1, requires_grad=True)
+
+    def step():
+        f = feat.clone().requires_grad_(True)
+        v = vecs.clone().requires_grad_(True)
+        scale.grad = None
+        bias.grad = None
+        return TP.train_step(waves_bsl, f, v, scale, bias)
+    return step
+
+
+def run_cpu_baseline(B, reps, budget_s=30.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_factory(B, 4242)
+    step()                                                        # warm-up (first-shape FFT planning etc.)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return B / min(times), times
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    B = 16
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_factory(B, 4242)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    cores = torch.get_num_threads()
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="fp32", data="synthetic", impl="reference",
+                config=dict(workload="C2 MUSIC N=2 train step (STFT+prepare+synth K=32+sigmoid+weighted BCE+backward), reference torch "
+                                     "path on host cores", batch_per_step=B, num_mix=N_SRC, K=K_CH, stft="1022/256", grid="256x256"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{B} mixtures per step x {args.steps} steps of the C2 workload; torch.stft stands in for librosa "
+                                         f"(absent); reference InnerProd/BCELoss call sequence restated in oracle/torch_ref_path.py"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def main_ours(args, rank, world, local):
+    import torch.distributed as dist
+    import avsep_b200 as av
+    from avsep_b200 import parallel
+
+    torch.cuda.set_device(local)
+    av.device_check()
+    dev = torch.device("cuda", local)
+    B, N, K = B_PER_GPU, N_SRC, K_CH
+    pk = peaks()
+
+    waves_host = make_waves(B, N, 1234 + rank).pin_memory()                       # [N+1, B, L]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    feat = torch.randn((B, K, 256, 256), device=dev, generator=g)
+    vecs_host = torch.sigmoid(torch.randn((B, N, K), generator=torch.Generator().manual_seed(7 + rank))).pin_memory()
+    scale = torch.ones(K, device=dev)
+    bias = torch.zeros(1, device=dev)
+    waves_dev = waves_host.to(dev)
+    vecs_dev = vecs_host.to(dev)
+    dfeat = torch.empty_like(feat)
+    dvecs = torch.empty((B, N, K), device=dev)
+    dscale = torch.empty(K, device=dev)
+    dbias = torch.empty(1, device=dev)
+    loss = torch.zeros(1, device=dev)
+    dvecs_host = torch.empty((B, N, K)).pin_memory()
+    step = av.Step(B, N, K, L)
+    eval_mode = args.workload == "eval"
+    wav_dev = torch.empty((B, N + 1, 65280), device=dev) if eval_mode else None
+    wav_host = torch.empty((B, N + 1, 65280)).pin_memory() if eval_mode else None
+
+    def step_dev():
+        if eval_mode:
+            step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        else:
+            step.train_dev(waves_dev, vecs_dev, feat, scale, bias, dfeat, dvecs, dscale, dbias, loss)
+
+    def step_host():
+        if eval_mode:
+            step.eval_host(waves_host, vecs_host, feat, scale, bias, wav_host)
+            return 0.0
+        return step.train_host(waves_host, vecs_host, feat, scale, bias, dfeat, dvecs_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = av.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    launches = av.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(loss)
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI entry point (`e2e`) ---------------------------------------
+    for _ in range(3):
+        step_host()
+    barrier()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_host = step_host()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = parallel.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), device=dev)
+    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = waves_host.numel() * 4 + vecs_host.numel() * 4
+    d2h = (wav_host.numel() * 4) if eval_mode else (4 + dvecs_host.numel() * 4)
+    if world > 1:
+        gl = parallel.global_mean_loss(torch.tensor(loss_val, device=dev), B)   # the path's only collective: 2 scalars
+        loss_val = float(gl)
+
+    # ---- per-kernel roofline (rank 0), each kernel timed alone with CUDA events ---------------------------
+    kernels = []
+    roofline = None
+    if rank == 0 and not eval_mode:
+        lib, stream = av._lib.lib, torch.cuda.current_stream().cuda_stream
+        plan = lib.avsep_step_plan(step._h)
+        S = (N + 1) * B
+        mag = torch.empty((S, 512, T), device=dev)
+        gt = step.buffer("gt_masks")
+        wts = step.buffer("weights")
+        pred = torch.empty((N, B, HW), device=dev)
+        scratch = torch.empty(int(lib.avsep_synth_scratch_bytes(B, N, K, HW)), dtype=torch.uint8, device=dev)
+        one = torch.ones(1, device=dev)
+        mags = av._lib.ptr_array([mag.data_ptr() + (1 + n) * B * 512 * T * 4 for n in range(N)])
+        outs = [torch.empty((B, 256, T), device=dev) for _ in range(3 + 2 * N)]
+        mw = av._lib.ptr_array([outs[3 + n].data_ptr() for n in range(N)])
+        gg = av._lib.ptr_array([outs[3 + N + n].data_ptr() for n in range(N)])
+        chk = av._lib.check
+        t_stft = time_calls(lambda: chk(lib.avsep_stft(plan, waves_dev.data_ptr(), S, mag.data_ptr(), None, None, None, stream)), 10)
+        t_gemm = time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan, 0, S, mag.data_ptr(), stream)), 10)
+        t_prep = time_calls(lambda: chk(lib.avsep_prepare(mag.data_ptr(), mags, N, B, T, 1, 1, 1, outs[0].data_ptr(), mw,
+                                                          outs[1].data_ptr(), outs[2].data_ptr(), gg, stream)), 10)
+        t_fwd = time_calls(lambda: chk(lib.avsep_synth_forward(feat.data_ptr(), vecs_dev.data_ptr(), scale.data_ptr(), bias.data_ptr(),
+                                                               B, N, K, HW, 1, pred.data_ptr(), 3, gt.data_ptr(), wts.data_ptr(),
+                                                               loss.data_ptr(), scratch.data_ptr(), stream)), 10)
+        t_bwd = time_calls(lambda: chk(lib.avsep_synth_backward(feat.data_ptr(), vecs_dev.data_ptr(), scale.data_ptr(), B, N, K, HW, 1, 3,
+                                                                pred.data_ptr(), gt.data_ptr(), wts.data_ptr(), one.data_ptr(), None,
+                                                                dfeat.data_ptr(), dvecs.data_ptr(), dscale.data_ptr(), dbias.data_ptr(),
+                                                                scratch.data_ptr(), stream)), 10)
+        times = {"dft_gemm_fwd": t_gemm, "wave_split": max(t_stft - t_gemm, 1e-6), "prepare": t_prep,
+                 "synth_fwd_loss": t_fwd, "synth_bwd": t_bwd}
+        tot = sum(times.values())
+        for name, ms in times.items():
+            a = ALG[name]
+            if a["bound"] == "tensor":
+                ach = a["flops"] * B / (ms * 1e-3) / 1e12
+                kernels.append(dict(kernel=name, ms=ms, share=ms / tot, bound="tensor", achieved=ach, peak=pk["tensor"],
+                                    unit="TFLOP/s", frac=ach / pk["tensor"], executed_tflops=3 * ach,
+                                    tensor_pipe_frac=3 * ach / pk["tensor"]))
+            else:
+                ach = a["bytes"] * B / (ms * 1e-3) / 1e9
+                kernels.append(dict(kernel=name, ms=ms, share=ms / tot, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s",
+                                    frac=ach / pk["hbm"]))
+        top = max(kernels, key=lambda k: k["ms"])
+        roofline = dict(kernel=top["kernel"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"],
+                        frac=top["frac"], traffic=None, peak_source=pk["source"],
+                        note=("algorithmic fp32-equivalent FLOPs (0.536 GFLOP/signal); the bf16x3 split executes 3x that on the "
+                              "tensor pipe, see kernels[].tensor_pipe_frac" if top["bound"] == "tensor" else
+                              "algorithmic bytes per SURVEY.md section 8(d)"))
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample ------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, times_cpu = run_cpu_baseline(16, 5, budget_s=25.0)
+            cpu_baseline = dict(value=v, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                                sample=f"16 mixtures per step, best of {len(times_cpu)} steps after 1 warm-up, same C2 train-step workload "
+                                       f"(oracle/torch_ref_path.py: the reference's torch call sequence; torch.stft for the absent librosa)")
+        except Exception as e:                                                    # pragma: no cover
+            cpu_baseline = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port", sample=f"failed: {e}")
+
+    if rank == 0:
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="fp32 (DFT GEMM: bf16x3 split operands, fp32 TMEM accumulate)", data="synthetic",
+            config=dict(workload=("C3-style eval step (STFT+prepare+synth+sigmoid+BCE+unwarp+mask+iSTFT)" if eval_mode else
+                                  "C2 MUSIC N=2 train step: STFT(3 signals)+prepare+synth K=32+sigmoid+weighted BCE+backward"),
+                        batch_per_gpu=B, global_batch=B * world, num_mix=N, K=K, samples=L, stft="1022/256", grid="256x256",
+                        parallelism=f"batch-sharded x{world}, no data-path collective",
+                        l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
+                     api="avsep_step_train_host (C-ABI, pinned host waveforms + K-vectors in, loss + dvecs out)"),
+            gpu_launches=int(launches), clocks=clocks, loss=loss_val, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline)
+        print(json.dumps(line), flush=True)
+    step.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "eval"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if world > 1:
+        from avsep_b200 import parallel
+        parallel.init_from_env("nccl")
+    main_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -265,8 +265,16 @@ def sigmoid(z):
 
 
 def sigmoid_f32(z):
-    """torch.sigmoid on float32 input: result rounded to float32 (saturates to exactly 0/1)."""
-    return sigmoid(np.asarray(z, dtype=np.float32)).astype(np.float32)
+    """torch.sigmoid on float32 input: 1 / (1 + exp(-z)) evaluated IN float32, as ATen does.
+
+    The float32 evaluation matters: for z >~ 16.7 the sum 1 + exp(-z) rounds to 1 and the result
+    saturates to exactly 1.0 (a correctly rounded float64 sigmoid would give 0.99999994), which is
+    what makes the reference's BCE term clamp to 100 * w there.
+    """
+    z = np.asarray(z, dtype=np.float32)
+    with np.errstate(over="ignore"):
+        e = np.exp(-z)
+    return (np.float32(1) / (np.float32(1) + e)).astype(np.float32)
 
 
 # ----------------------------------------------------------------------------

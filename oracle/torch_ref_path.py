@@ -106,7 +106,7 @@ def train_step(waves, feat_sound, vecs, scale, bias):
     preds = [torch.sigmoid(innerprod(vecs[:, n, :], feat_sound, scale, bias)) for n in range(S - 1)]
     err = bce_list(preds, gt_masks, weights)
     err.backward()
-    return float(err)
+    return float(err.detach())
 
 
 def eval_step(waves, feat_sound, vecs, scale, bias, binary_mask=True, mask_thres=0.5):

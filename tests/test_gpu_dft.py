@@ -1,0 +1,267 @@
+"""GPU parity of the tcgen05 DFT GEMM path (K1 STFT, K4 iSTFT / separate) against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): spectrogram / waveform max-norm relative error <= 1e-4.
+The split-precision (bf16 x 3) GEMM is expected to land around 4e-6.
+All calls go through the C-ABI (ctypes) of libavsep_b200.so.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import np_oracle as O
+
+import avsep_b200 as av
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+L = 65535
+
+
+def _signals(S, seed=1234, length=L):
+    w = O.synth_sources(1, S, L=length, seed=seed)[0]          # [S, L], each already / S
+    return np.ascontiguousarray(w * S * 0.5)
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+def _basis_expected(inverse):
+    n = np.arange(1022)
+    win = O.hann_periodic(1022)
+    out = np.zeros((1024, 1024))
+    R = np.arange(1024)
+    m, q = R >> 7, (R >> 5) & 3
+    if not inverse:
+        part, i = (R >> 4) & 1, R & 15
+        f = 64 * m + 16 * q + i
+        ang = 2 * np.pi * ((f[:, None] * n[None, :]) % 1022) / 1022.0
+        out[:, :1022] = np.where(part[:, None] == 0, np.cos(ang), -np.sin(ang)) * win[None, :]
+    else:
+        jj = R & 31
+        nn = 32 * m + jj + 256 * q
+        ok = nn < 1022
+        f = np.arange(512)
+        c = np.where((f == 0) | (f == 511), 1.0, 2.0)
+        nv = np.where(ok, nn, 0)
+        ang = 2 * np.pi * ((nv[:, None] * f[None, :]) % 1022) / 1022.0
+        w = np.where(ok, win[nv], 0.0)[:, None]
+        out[:, :512] = w * c[None, :] * np.cos(ang) / 1022.0
+        out[:, 512:] = -w * c[None, :] * np.sin(ang) / 1022.0
+    return out
+
+
+def test_basis_tables():
+    plan = av.Plan(1, L)
+    for inverse in (0, 1):
+        got = np.zeros((1024, 1024), dtype=np.float32)
+        av._lib.check(av._lib.lib.avsep_debug_basis(plan.handle, inverse, got.ctypes.data))
+        assert relerr(got, _basis_expected(inverse)) < 2e-5          # bf16 hi + lo = 16 significant bits
+    plan.close()
+
+
+@pytest.mark.parametrize("kblock,overlap", [(32, True), (64, True), (32, False)])
+def test_raw_gemm_matches_staged_operands(kblock, overlap):
+    """Isolates the tensor-core pipeline: raw accumulators vs (hi+lo basis) @ (hi+lo staged frames) in float64."""
+    if not overlap:
+        os.environ["AVSEP_DFT_NO_OVERLAP_TMA"] = "1"
+    try:
+        plan = av.Plan(3, L)
+    finally:
+        os.environ.pop("AVSEP_DFT_NO_OVERLAP_TMA", None)
+    plan.set_kblock(kblock)
+    S = 3
+    w = torch.from_numpy(_signals(S)).cuda()
+    mag, _ = av.stft(w, plan=plan)
+    _sync()
+    T = plan.frames
+    raw = torch.empty((S, 1024, T), device="cuda")
+    av._lib.check(av._lib.lib.avsep_debug_raw_gemm(plan.handle, 0, S, raw.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    _sync()
+    basis = np.zeros((1024, 1024), dtype=np.float32)
+    av._lib.check(av._lib.lib.avsep_debug_basis(plan.handle, 0, basis.ctypes.data))
+    for s in (0, S - 1):
+        frames = np.zeros((T, 1024), dtype=np.float32)
+        av._lib.check(av._lib.lib.avsep_debug_staged_frames(plan.handle, s, frames.ctypes.data))
+        # staged operand = reflect-padded wave, 16 significant bits
+        pad = np.pad(w[s].cpu().numpy().astype(np.float64), 511, mode="reflect")
+        exp_frames = np.stack([pad[256 * t:256 * t + 1022] for t in range(T)])
+        assert relerr(frames[:, :1022], exp_frames) < 2e-5
+        expect = basis.astype(np.float64) @ frames.astype(np.float64).T
+        assert relerr(raw[s].cpu().numpy(), expect) < 1e-5, f"kblock={kblock} overlap={overlap} signal {s}"
+    plan.close()
+
+
+def test_stft_vs_oracle():
+    S = 3
+    wav = _signals(S)
+    mag, ph, re, im = av.stft(torch.from_numpy(wav).cuda(), complex_parts=True)
+    _sync()
+    assert mag.shape == (S, 512, 256) and ph.shape == mag.shape
+    for s in range(S):
+        spec = O.stft_complex(wav[s])
+        amp_o, _ = O.stft_magphase(wav[s])
+        assert relerr(mag[s].cpu().numpy(), amp_o) < TOL
+        got = re[s].cpu().numpy().astype(np.float64) + 1j * im[s].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(got - spec)) / np.max(np.abs(spec)) < TOL
+        # phase is compared through the reconstructed spectrum (atan2 branch cut)
+        rec = mag[s].cpu().numpy().astype(np.float64) * np.exp(1j * ph[s].cpu().numpy().astype(np.float64))
+        assert np.max(np.abs(rec - spec)) / np.max(np.abs(spec)) < TOL
+    err = relerr(mag[0].cpu().numpy(), O.stft_magphase(wav[0])[0])
+    print(f"stft max-norm relative error {err:.3e}")
+
+
+def test_stft_golden_fixture(golden):
+    g = golden("stft")
+    src = O.synth_sources(1, 2, seed=1234)[0]
+    mix = (src[0] + src[1]).astype(np.float32)
+    mag, ph = av.stft(torch.from_numpy(np.stack([mix, src[0]])).cuda())
+    fr = g["frames"]
+    assert relerr(mag[0].cpu().numpy()[:, fr], g["amp_mix"]) < TOL
+    assert relerr(mag[1].cpu().numpy()[:, fr], g["amp_src0"]) < TOL
+    rec = mag[0].cpu().numpy()[:, fr].astype(np.float64) * np.exp(1j * ph[0].cpu().numpy()[:, fr].astype(np.float64))
+    ref = g["amp_mix"].astype(np.float64) * np.exp(1j * g["phase_mix"].astype(np.float64))
+    assert np.max(np.abs(rec - ref)) / np.max(np.abs(ref)) < TOL
+
+
+@pytest.mark.parametrize("length", [3000, 512, 70001])
+def test_stft_ragged_lengths(length, golden):
+    """Edge cases: short clips (T < one tile), clips longer than one 256-frame tile."""
+    wav = _signals(2, seed=5, length=length)
+    mag, ph = av.stft(torch.from_numpy(wav).cuda())
+    T = O.n_frames(length)
+    assert mag.shape == (2, 512, T)
+    for s in range(2):
+        amp_o, _ = O.stft_magphase(wav[s])
+        assert relerr(mag[s].cpu().numpy(), amp_o) < TOL
+    if length == 3000:
+        g = golden("stft")
+        src = O.synth_sources(1, 2, seed=1234)[0]
+        m2, _ = av.stft(torch.from_numpy(src[1][:3000].copy()).cuda())
+        assert relerr(m2.cpu().numpy(), g["amp_short"]) < TOL
+
+
+def test_stft_single_and_empty_batch():
+    wav = _signals(1)
+    m1, p1 = av.stft(torch.from_numpy(wav[0]).cuda())
+    assert m1.shape == (512, 256)
+    assert relerr(m1.cpu().numpy(), O.stft_magphase(wav[0])[0]) < TOL
+    with pytest.raises(av.AvsepError):
+        av.stft(torch.zeros(1, 300, device="cuda"))                 # shorter than the reflect padding
+    with pytest.raises(av.AvsepError):
+        av.stft(torch.zeros(2, L, device="cuda", dtype=torch.float64))
+
+
+def test_istft_vs_oracle():
+    wav = _signals(2, seed=9)
+    amp, ph = zip(*[O.stft_magphase(w) for w in wav])
+    amp, ph = np.stack(amp), np.stack(ph)
+    mask = (np.random.default_rng(51).random((2, 512, 256)) > 0.4).astype(np.float32)
+    out = av.istft(torch.from_numpy(amp * mask).cuda(), torch.from_numpy(ph).cuda())
+    _sync()
+    assert out.shape == (2, 65280)
+    for s in range(2):
+        ref = O.istft_reconstruction(amp[s] * mask[s], ph[s])
+        e = relerr(out[s].cpu().numpy(), ref)
+        assert e < TOL, e
+    # clip to [-1, 1] (utils.py:104)
+    loud = av.istft(torch.from_numpy(amp * 40).cuda(), torch.from_numpy(ph).cuda())
+    assert float(loud.abs().max()) <= 1.0
+    ref = O.istft_reconstruction(amp[0] * 40, ph[0])
+    assert relerr(loud[0].cpu().numpy(), ref) < TOL
+
+
+def test_istft_golden_fixture(golden):
+    g = golden("stft")
+    src = O.synth_sources(1, 2, seed=1234)[0]
+    mix = (src[0] + src[1]).astype(np.float32)
+    amp, ph = O.stft_magphase(mix)
+    mask = (np.random.default_rng(51).random((512, 256)) > 0.4).astype(np.float32)
+    out = av.istft(torch.from_numpy((amp * mask)[None]).cuda(), torch.from_numpy(ph[None]).cuda())[0].cpu().numpy()
+    assert out.shape[0] == int(g["istft_len"])
+    scale = max(np.max(np.abs(g["istft_masked_head"])), np.max(np.abs(g["istft_masked_mid"])), np.max(np.abs(g["istft_masked_tail"])))
+    assert np.max(np.abs(out[:4096] - g["istft_masked_head"])) / scale < TOL
+    assert np.max(np.abs(out[30000:34096] - g["istft_masked_mid"])) / scale < TOL
+    assert np.max(np.abs(out[-4096:] - g["istft_masked_tail"])) / scale < TOL
+
+
+def test_istft_reconstruction_dropin():
+    """utils.istft_reconstruction signature: numpy in, float64 numpy out."""
+    wav = _signals(1, seed=3)[0]
+    amp, ph = O.stft_magphase(wav)
+    out = av.istft_reconstruction(amp, ph, hop_length=256)
+    assert out.dtype == np.float64 and out.shape == (65280,)
+    assert relerr(out, O.istft_reconstruction(amp, ph)) < TOL
+    a2, p2 = av._stft(wav)
+    assert a2.shape == (512, 256) and relerr(a2.cpu().numpy(), amp) < TOL
+
+
+def _block_masks(rng, N, B, H=256, T=256, lo=0.2, hi=0.9, blk=8):
+    small = rng.random((N, B, H // blk, T // blk)) > 0.5
+    m = np.where(small, hi, lo).astype(np.float32)
+    return np.repeat(np.repeat(m, blk, axis=2), blk, axis=3)
+
+
+@pytest.mark.parametrize("binary,log_freq", [(True, True), (False, True), (True, False)])
+def test_separate_vs_oracle(binary, log_freq):
+    B, N = 2, 2
+    rng = np.random.default_rng(77)
+    src = O.synth_sources(B, N, seed=77)
+    mix = src.sum(axis=1).astype(np.float32)
+    amp, ph = zip(*[O.stft_magphase(m) for m in mix])
+    amp, ph = np.stack(amp)[:, None], np.stack(ph)[:, None]
+    H = 256 if log_freq else 512
+    if binary:
+        masks = _block_masks(rng, N, B, H=H)
+    else:
+        masks = rng.random((N, B, H, 256)).astype(np.float32)
+    pred = [torch.from_numpy(masks[n][:, None]).cuda() for n in range(N)]
+    out = av.separate(pred, torch.from_numpy(amp).cuda(), torch.from_numpy(ph).cuda(), log_freq=log_freq,
+                      binary_mask=binary, mask_thres=0.5)
+    _sync()
+    assert out.shape == (B, N + 1, 65280)
+    mix_o, pred_o, _ = O.separate(amp, ph, [masks[n][:, None] for n in range(N)], log_freq=log_freq, binary_mask=binary)
+    scale = np.max(np.abs(mix_o))
+    got = out.cpu().numpy()
+    assert np.max(np.abs(got[:, 0] - mix_o)) / scale < TOL
+    for n in range(N):
+        assert np.max(np.abs(got[:, 1 + n] - pred_o[:, n])) / scale < TOL
+
+
+def test_separate_with_complex_parts_equals_magphase():
+    B, N = 1, 2
+    src = O.synth_sources(B, N, seed=8)
+    mix = torch.from_numpy(src.sum(axis=1).astype(np.float32)).cuda()
+    mag, ph, re, im = av.stft(mix, complex_parts=True)
+    masks = torch.rand((N, B, 256, 256), device="cuda")
+    a = av.separate(masks, mag, ph, binary_mask=False)
+    b = av.separate(masks, None, None, re_mix=re, im_mix=im, binary_mask=False)
+    assert float((a - b).abs().max()) / float(a.abs().max()) < 2e-5
+
+
+def test_roundtrip_and_linearity_at_full_batch():
+    """Size-independent properties at BASELINE config sizes (B=80, N=2 -> 240 signals):
+    iSTFT(STFT(x)) == x[:65280] and STFT(a + b) == STFT(a) + STFT(b)."""
+    B, N = 80, 2
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    src = (torch.rand((N, B, L), device="cuda", generator=g) - 0.5) * 0.8
+    mix = src.sum(dim=0)
+    waves = torch.cat([mix[None], src], dim=0).reshape((N + 1) * B, L)
+    mag, ph, re, im = av.stft(waves, complex_parts=True)
+    rec = av.istft(mag, ph)
+    _sync()
+    err = float((rec - waves[:, :65280]).abs().max())
+    assert err < 1e-4 * float(waves.abs().max()) * 10, err          # fp32 round trip: ~1e-6 absolute
+    assert err < 2e-5
+    re = re.view(N + 1, B, 512, 256)
+    im = im.view(N + 1, B, 512, 256)
+    lin = max(float((re[0] - re[1] - re[2]).abs().max()), float((im[0] - im[1] - im[2]).abs().max()))
+    assert lin / float(mag.max()) < 2e-5
+    # determinism: same input, same bits
+    mag2, _ = av.stft(waves, phase=False)
+    assert torch.equal(mag, mag2)
+    rec2 = av.istft(mag, ph)
+    assert torch.equal(rec, rec2)

@@ -1,0 +1,303 @@
+"""GPU parity of the HBM-bound kernels (K2 warp / prepare, K3 synthesizer + loss fwd/bwd, criterion, PIT)
+against the CPU oracle and the golden vectors produced by the real reference code.
+
+Tolerance (north_star): mask / spectrogram max-norm relative error <= 1e-4 (these kernels land ~1e-6);
+thresholded outputs are compared by mismatch fraction (a 1-ulp difference may flip an exact tie).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import relerr
+from oracle import np_oracle as O
+
+import avsep_b200 as av
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _rng_inputs(seed, *shapes):
+    g = np.random.default_rng(seed)
+    return [g.standard_normal(s).astype(np.float32) for s in shapes]
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------------
+def test_warp_matches_golden_and_oracle(golden):
+    g = golden("grid_sample")
+    (xw,) = _rng_inputs(11, (2, 1, 512, 256))
+    xw = np.abs(xw)
+    yw = av.warp(_cuda(xw), 256, warp=True).cpu().numpy()
+    assert yw.shape == (2, 1, 256, 256)
+    assert relerr(yw[1], g["warp_out_b1"]) < TOL
+    assert relerr(yw, O.log_freq_warp(xw, 256, True)) < 2e-6
+    (xu,) = _rng_inputs(12, (2, 1, 256, 256))
+    yu = av.warp(_cuda(xu), 512, warp=False).cpu().numpy()
+    assert relerr(yu[1], g["unwarp_out_b1"]) < TOL
+    assert relerr(yu, O.log_freq_warp(xu, 512, False)) < 2e-6
+    (xs,) = _rng_inputs(13, (1, 1, 512, 24))
+    assert relerr(av.warp(_cuda(xs), 256, True).cpu().numpy(), g["warp_T24"]) < TOL
+
+
+def test_warp_equals_torch_grid_sample_on_gpu():
+    """The reference's own GPU path: F.grid_sample with the reference grid (main.py:62-64)."""
+    x = torch.rand((3, 1, 512, 256), device="cuda")
+    grid = torch.from_numpy(av.warpgrid(3, 256, 256, warp=True)).cuda()
+    ref = F.grid_sample(x, grid, align_corners=False)
+    assert float((av.warp(x, 256, True) - ref).abs().max()) < 2e-6
+    m = torch.rand((3, 1, 256, 256), device="cuda")
+    grid = torch.from_numpy(av.warpgrid(3, 512, 256, warp=False)).cuda()
+    ref = F.grid_sample(m, grid, align_corners=False)
+    assert float((av.warp(m, 512, False) - ref).abs().max()) < 2e-6
+    # odd widths and a single column
+    for T in (1, 7, 250, 300):
+        x = torch.rand((2, 1, 512, T), device="cuda")
+        grid = torch.from_numpy(av.warpgrid(2, 256, T, warp=True)).cuda()
+        assert float((av.warp(x, 256, True) - F.grid_sample(x, grid, align_corners=False)).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("binary,weighted", [(True, True), (False, False)])
+def test_prepare_matches_golden(golden, binary, weighted):
+    g = golden("prepare")
+    tag = "bin_w" if binary else "ratio_now"
+    r = np.random.default_rng(21)
+    mags = [np.abs(r.standard_normal((2, 1, 512, 64))).astype(np.float32) * 3 for _ in range(2)]
+    mag_mix = (mags[0] + mags[1] * np.float32(0.7)).astype(np.float32)
+    mags_w, mix_w, log_mix, gts, weights = av.ops.prepare(_cuda(mag_mix), [_cuda(m) for m in mags], log_freq=True,
+                                                          weighted_loss=weighted, binary_mask=binary)
+    assert relerr(mix_w.cpu().numpy(), g[f"{tag}_mag_mix"]) < TOL
+    assert relerr(mags_w[0].cpu().numpy(), g[f"{tag}_mags0"]) < TOL
+    assert relerr(mags_w[1].cpu().numpy(), g[f"{tag}_mags1"]) < TOL
+    assert relerr(log_mix.cpu().numpy(), g[f"{tag}_log"]) < TOL
+    assert relerr(weights.cpu().numpy(), g[f"{tag}_w"]) < TOL
+    for n in range(2):
+        if binary:
+            assert np.mean(gts[n].cpu().numpy() != g[f"{tag}_gt{n}"]) < 1e-4
+        else:
+            assert relerr(gts[n].cpu().numpy(), g[f"{tag}_gt{n}"]) < TOL
+
+
+def test_prepare_dropin_signature_and_edge_cases():
+    import types
+    B, N, T = 3, 3, 256
+    r = np.random.default_rng(2)
+    mags = [np.abs(r.standard_normal((B, 1, 512, T))).astype(np.float32) for _ in range(N)]
+    mags[1][0] = 0.0                                            # a silent source
+    mix = sum(mags).astype(np.float32)
+    mix[2] = 0.0                                                # a silent mixture: log(1e-10), weight clamp at 1e-3
+    batch = dict(mag_mix=_cuda(mix), mags=[_cuda(m) for m in mags])
+    args = types.SimpleNamespace(num_mix=N, log_freq=1, weighted_loss=1, binary_mask=1, fusion_type="none")
+    mags_w, mix_w, log_mix, gts, w = av.prepare(batch, args, False, False)
+    assert batch["mags"][0] is mags_w[0]                        # main.py:66 rebinds the list entries
+    o = O.prepare(mix, mags, log_freq=True, weighted_loss=True, binary_mask=True)
+    assert relerr(mix_w.cpu().numpy(), o["mag_mix"]) < 2e-6
+    assert relerr(log_mix.cpu().numpy(), o["log_mag_mix"]) < 2e-6
+    assert relerr(w.cpu().numpy(), o["weights"]) < 2e-6
+    assert float(w.min()) >= 1e-3 - 1e-9
+    for n in range(N):
+        assert np.mean(gts[n].cpu().numpy() != o["gt_masks"][n]) < 1e-4
+    # log_freq off: no resample at all (main.py:60)
+    args.log_freq = 0
+    batch = dict(mag_mix=_cuda(mix), mags=[_cuda(m) for m in mags])
+    _, mix2, log2, _, _ = av.prepare(batch, args, False, False)
+    assert mix2.shape == (B, 1, 512, T)
+    assert torch.equal(mix2, _cuda(mix) + 1e-10)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3
+# ---------------------------------------------------------------------------------------------------
+def _synth_inputs():
+    B, K, H, W, N = 2, 32, 16, 24, 2
+    g = np.random.default_rng(31)
+    feat = g.standard_normal((B, K, H, W)).astype(np.float32)
+    vecs = (1 / (1 + np.exp(-g.standard_normal((B, N, K))))).astype(np.float32)
+    scale = (1 + 0.1 * g.standard_normal(K)).astype(np.float32)
+    bias = np.array([0.05], dtype=np.float32)
+    gts = [(g.random((B, 1, H, W)) > 0.5).astype(np.float32) for _ in range(N)]
+    wgt = np.clip(np.abs(g.standard_normal((B, 1, H, W))), 1e-3, 10).astype(np.float32)
+    fi = g.standard_normal((B, K, 3, 5)).astype(np.float32)
+    return feat, vecs, scale, bias, gts, wgt, fi
+
+
+def _module(scale, bias):
+    m = av.InnerProd(scale.shape[0]).cuda()
+    with torch.no_grad():
+        m.scale.copy_(_cuda(scale))
+        m.bias.copy_(_cuda(bias))
+    return m
+
+
+@pytest.mark.parametrize("kind", ["bce", "l1", "l2"])
+def test_fused_synth_loss_matches_reference_golden(golden, kind):
+    g = golden("synth")
+    feat, vecs, scale, bias, gts, wgt, _ = _synth_inputs()
+    m = _module(scale, bias)
+    tf = _cuda(feat).requires_grad_(True)
+    tv = _cuda(vecs).requires_grad_(True)
+    err, masks = m.forward_loss(tv, tf, [_cuda(t) for t in gts], _cuda(wgt), loss=kind)
+    err.backward()
+    assert abs(float(err) - float(g[f"{kind}_loss"])) / abs(float(g[f"{kind}_loss"])) < TOL
+    assert relerr(tf.grad.cpu().numpy(), g[f"{kind}_dfeat"]) < TOL
+    assert relerr(tv.grad.cpu().numpy(), g[f"{kind}_dvecs"]) < TOL
+    assert relerr(m.scale.grad.cpu().numpy(), g[f"{kind}_dscale"]) < TOL
+    assert abs(float(m.bias.grad) - float(g[f"{kind}_dbias"][0])) / abs(float(g[f"{kind}_dbias"][0])) < TOL
+    if kind == "bce":
+        assert relerr(masks[0].cpu().numpy(), g["pred0"]) < TOL and relerr(masks[1].cpu().numpy(), g["pred1"]) < TOL
+
+
+@pytest.mark.parametrize("kind", ["bce", "l1"])
+def test_unfused_dropin_path_matches_reference_golden(golden, kind):
+    """The reference's own call pattern (SoP++/main.py:203-209): per-source InnerProd, torch sigmoid, criterion."""
+    g = golden("synth")
+    feat, vecs, scale, bias, gts, wgt, fi = _synth_inputs()
+    m = _module(scale, bias)
+    tf = _cuda(feat).requires_grad_(True)
+    tv = _cuda(vecs).requires_grad_(True)
+    preds = [av.activate(m(tv[:, n, :], tf), "sigmoid") for n in range(2)]
+    crit = av.BCELoss() if kind == "bce" else av.L1Loss()
+    err = crit(preds, [_cuda(t) for t in gts], _cuda(wgt))
+    err.backward()
+    assert abs(float(err) - float(g[f"{kind}_loss"])) / abs(float(g[f"{kind}_loss"])) < TOL
+    assert relerr(tf.grad.cpu().numpy(), g[f"{kind}_dfeat"]) < TOL
+    assert relerr(tv.grad.cpu().numpy(), g[f"{kind}_dvecs"]) < TOL
+    assert relerr(m.scale.grad.cpu().numpy(), g[f"{kind}_dscale"]) < TOL
+    assert abs(float(m.bias.grad) - float(g[f"{kind}_dbias"][0])) / abs(float(g[f"{kind}_dbias"][0])) < TOL
+    with torch.no_grad():
+        assert relerr(m(_cuda(vecs[:, 0]), _cuda(feat)).cpu().numpy(), g["z"]) < TOL
+        assert relerr(m.forward_nosum(_cuda(vecs[:, 0]), _cuda(feat)).cpu().numpy(), g["z_nosum"]) < TOL
+        assert relerr(m.forward_pixelwise(_cuda(fi), _cuda(feat)).cpu().numpy(), g["z_pixelwise"]) < TOL
+        bnet = av.Bias().cuda()
+        bnet.bias.copy_(_cuda(bias))
+        assert relerr(bnet(_cuda(vecs[:, 1]), _cuda(feat)).cpu().numpy(), g["z_bias"]) < TOL
+
+
+@pytest.mark.parametrize("N,K,H,W,use_scale", [(1, 32, 256, 256, True), (3, 64, 32, 40, True), (4, 16, 8, 12, False),
+                                               (2, 33, 5, 7, True)])
+def test_synth_shapes_vs_oracle(N, K, H, W, use_scale):
+    """N = 1..4 sources, K not a multiple of the 32-channel chunk, odd spatial sizes (scalar-path forward)."""
+    B = 2
+    g = np.random.default_rng(100 + N)
+    feat = g.standard_normal((B, K, H, W)).astype(np.float32)
+    vecs = (1 / (1 + np.exp(-g.standard_normal((B, N, K))))).astype(np.float32)
+    scale = (1 + 0.1 * g.standard_normal(K)).astype(np.float32) if use_scale else None
+    bias = np.array([-0.1], dtype=np.float32)
+    gts = [(g.random((B, 1, H, W)) > 0.5).astype(np.float32) for _ in range(N)]
+    wgt = np.clip(np.abs(g.standard_normal((B, 1, H, W))), 1e-3, 10).astype(np.float32)
+    o = O.synth_loss_and_grads("bce", feat, vecs, scale, bias, gts, wgt)
+    tf = _cuda(feat).requires_grad_(True)
+    tv = _cuda(vecs).requires_grad_(True)
+    ts = _cuda(scale).requires_grad_(True) if use_scale else None
+    tb = _cuda(bias).requires_grad_(True)
+    if (H * W) % 4 == 0:
+        err, masks = av.synth_masks_loss(tf, tv, ts, tb, [_cuda(t) for t in gts], _cuda(wgt), loss="bce")
+        err.backward()
+        assert abs(float(err) - o["loss"]) / abs(o["loss"]) < TOL
+        assert relerr(tf.grad.cpu().numpy(), o["dfeat"]) < TOL
+        assert relerr(tv.grad.cpu().numpy(), o["dvecs"]) < TOL
+        if use_scale:
+            assert relerr(ts.grad.cpu().numpy(), o["dscale"]) < TOL
+        assert abs(float(tb.grad) - o["dbias"]) / abs(o["dbias"]) < TOL
+        for n in range(N):
+            assert relerr(masks[n].cpu().numpy(), o["preds"][n][:, 0]) < TOL
+    else:
+        masks = av.synth_masks(tf, tv, ts, tb, activation="sigmoid")
+        for n in range(N):
+            assert relerr(masks[n].detach().cpu().numpy(), o["preds"][n][:, 0]) < TOL
+        with pytest.raises(av.AvsepError):
+            masks.sum().backward()                                # backward needs H*W % 4 == 0
+
+
+def test_bce_saturation_semantics_on_gpu(golden):
+    """z = +-40 etc.: loss term 100 * w, gradient exactly zero where sigmoid saturates."""
+    g = golden("synth")
+    z, t = g["sat_z"], g["sat_t"]
+    n = z.shape[0]
+    # one channel, vec = 1, feat = z  =>  logits = z
+    feat = np.zeros((1, 1, 1, 8), dtype=np.float32)
+    feat[0, 0, 0, :n] = z
+    gt = np.zeros((1, 1, 1, 8), dtype=np.float32)
+    gt[0, 0, 0, :n] = t
+    w = np.zeros((1, 1, 1, 8), dtype=np.float32)
+    w[0, 0, 0, :n] = 2.0
+    tf = _cuda(feat).requires_grad_(True)
+    err, _ = av.synth_masks_loss(tf, torch.ones((1, 1, 1), device="cuda"), None, None, [_cuda(gt)], _cuda(w), loss="bce")
+    err.backward()
+    assert abs(float(err) * 8 - float(g["sat_loss"])) / float(g["sat_loss"]) < 1e-5
+    grad = tf.grad.cpu().numpy()[0, 0, 0, :n] * 8
+    assert grad[0] == 0.0 and grad[3] == 0.0
+    assert np.allclose(grad, g["sat_grad"], rtol=1e-4, atol=1e-12)
+
+
+def test_synth_full_size_against_stock_torch_gpu_path():
+    """Full 256x256, K=32 grid: our kernels vs the reference's own library calls (bmm + sigmoid + BCE) on the GPU."""
+    B, N, K = 4, 2, 32
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    feat = torch.randn((B, K, 256, 256), device="cuda", generator=gen)
+    vecs = torch.sigmoid(torch.randn((B, N, K), device="cuda", generator=gen))
+    gts = [(torch.rand((B, 1, 256, 256), device="cuda", generator=gen) > 0.5).float() for _ in range(N)]
+    w = torch.rand((B, 1, 256, 256), device="cuda", generator=gen).clamp_(1e-3, 10)
+    m = av.InnerProd(K).cuda()
+    f1 = feat.clone().requires_grad_(True)
+    v1 = vecs.clone().requires_grad_(True)
+    err, masks = m.forward_loss(v1, f1, gts, w, loss="bce")
+    err.backward()
+    f2 = feat.clone().requires_grad_(True)
+    v2 = vecs.clone().requires_grad_(True)
+    scale = torch.ones(K, device="cuda", requires_grad=True)
+    bias = torch.zeros(1, device="cuda", requires_grad=True)
+    preds = [torch.sigmoid(torch.bmm((v2[:, n, :] * scale).view(B, 1, K), f2.view(B, K, -1)).view(B, 1, 256, 256) + bias)
+             for n in range(N)]
+    ref = torch.mean(torch.stack([F.binary_cross_entropy(p, t, weight=w) for p, t in zip(preds, gts)]))
+    ref.backward()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert abs(float(err) - float(ref)) / float(ref) < TOL
+    assert rel(f1.grad, f2.grad) < TOL and rel(v1.grad, v2.grad) < TOL
+    assert rel(m.scale.grad, scale.grad) < TOL and rel(m.bias.grad, bias.grad) < TOL
+    assert rel(masks[1], preds[1].detach()) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# criterion / PIT
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,cls", [("bce", "BCELoss"), ("l1", "L1Loss"), ("l2", "L2Loss")])
+def test_criterion_list_and_tensor_forms(kind, cls):
+    g = np.random.default_rng(5)
+    shape = (3, 1, 19, 17)                                     # numel = 969, not a multiple of 4
+    preds = [g.random(shape).astype(np.float32) * 0.98 + 0.01 for _ in range(3)]
+    tgts = [(g.random(shape) > 0.5).astype(np.float32) for _ in range(3)]
+    w = np.abs(g.standard_normal(shape)).astype(np.float32)
+    crit = getattr(av, cls)()
+    tp = [_cuda(p).requires_grad_(True) for p in preds]
+    err = crit(tp, [_cuda(t) for t in tgts], _cuda(w))
+    err.backward()
+    assert abs(float(err) - O.criterion(kind, preds, tgts, w)) / O.criterion(kind, preds, tgts, w) < 1e-5
+    for n in range(3):
+        ref = O.loss_grad_wrt_pred(kind, preds[n], tgts[n], w, preds[n].size, 3)
+        assert relerr(tp[n].grad.cpu().numpy(), ref) < 1e-5
+    # tensor form, no weight (criterion.py:20-23)
+    e2 = crit(_cuda(preds[0]), _cuda(tgts[0]))
+    assert abs(float(e2) - O.criterion(kind, preds[0], tgts[0], None)) / O.criterion(kind, preds[0], tgts[0], None) < 1e-5
+
+
+def test_pit_matches_reference_golden(golden):
+    g = golden("pit")
+    pw = av.PitWrapper("bce")
+    for S in (2, 3):
+        r = np.random.default_rng(40 + S)
+        pr = r.random((3, 12, 10, S)).astype(np.float32) * 0.98 + 0.01
+        tg = (r.random((3, 12, 10, S)) > 0.5).astype(np.float32)
+        pr[1] = np.clip(tg[1][..., ::-1] * 0.9 + 0.05, 0.01, 0.99)
+        ww = np.repeat(np.abs(r.standard_normal((3, 12, 10, 1))).astype(np.float32), S, axis=-1)
+        loss, perms = pw(_cuda(pr), _cuda(tg), _cuda(ww))
+        assert relerr(loss.cpu().numpy(), g[f"S{S}_loss"]) < 1e-5
+        assert np.array_equal(np.asarray(perms), g[f"S{S}_perms"])
+        re = pw.reorder_tensor(_cuda(pr), perms).cpu().numpy()
+        assert np.array_equal(re, O.pit_reorder(pr, perms))

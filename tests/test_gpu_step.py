@@ -1,0 +1,162 @@
+"""GPU parity of the fused end-to-end steps (what bench.py times) and of the calc_metrics drop-in,
+including the SDR / SIR / SAR criterion of the north star (per clip within 0.01 dB of the oracle)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import bss_eval as BSS
+from oracle import np_oracle as O
+
+import avsep_b200 as av
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+L = 65535
+
+
+def _inputs(B, N, K=32, seed=1234):
+    src = O.synth_sources(B, N, seed=seed)                      # [B, N, L]
+    mix = src.sum(axis=1).astype(np.float32)
+    waves = np.concatenate([mix[None], np.transpose(src, (1, 0, 2))], axis=0)   # [N+1, B, L]
+    g = np.random.default_rng(seed + 1)
+    feat = g.standard_normal((B, K, 256, 256)).astype(np.float32)
+    vecs = (1 / (1 + np.exp(-g.standard_normal((B, N, K))))).astype(np.float32)
+    scale = (1 + 0.05 * g.standard_normal(K)).astype(np.float32)
+    bias = np.array([0.02], dtype=np.float32)
+    return np.ascontiguousarray(waves), feat, vecs, scale, bias
+
+
+def _oracle_front(waves, N, B):
+    amp = np.stack([np.stack([O.stft_magphase(waves[j, b])[0] for b in range(B)]) for j in range(N + 1)])  # [N+1,B,512,256]
+    prep = O.prepare(amp[0][:, None], [amp[1 + n][:, None] for n in range(N)])
+    return amp, prep
+
+
+def test_train_step_vs_oracle():
+    B, N, K = 2, 2, 32
+    waves, feat, vecs, scale, bias = _inputs(B, N, K)
+    amp, prep = _oracle_front(waves, N, B)
+    st = av.Step(B, N, K, L)
+    c = lambda a: torch.from_numpy(a).cuda()
+    dfeat = torch.empty((B, K, 256, 256), device="cuda")
+    dvecs = torch.empty((B, N, K), device="cuda")
+    dscale = torch.empty(K, device="cuda")
+    dbias = torch.empty(1, device="cuda")
+    loss = torch.empty(1, device="cuda")
+    tfeat = c(feat)
+    st.train_dev(c(waves), c(vecs), tfeat, c(scale), c(bias), dfeat, dvecs, dscale, dbias, loss)
+    torch.cuda.synchronize()
+    # front end
+    assert relerr(st.buffer("mag").cpu().numpy().reshape(N + 1, B, 512, 256), amp) < TOL
+    assert relerr(st.buffer("mag_mix_w").cpu().numpy(), prep["mag_mix"]) < TOL
+    assert relerr(st.buffer("log_mag_mix").cpu().numpy(), prep["log_mag_mix"]) < TOL
+    assert relerr(st.buffer("weights").cpu().numpy(), prep["weights"]) < TOL
+    gt_gpu = st.buffer("gt_masks").cpu().numpy()
+    mism = np.mean(gt_gpu != np.stack(prep["gt_masks"]))
+    assert mism < 1e-3, mism                                      # ties of m > 0.5 * mix at the 4e-6 STFT error level
+    # back end on the GPU's own gt/weights (so a flipped tie does not leak into the comparison)
+    o = O.synth_loss_and_grads("bce", feat, vecs, scale, bias, [gt_gpu[n] for n in range(N)],
+                               st.buffer("weights").cpu().numpy())
+    assert abs(float(loss) - o["loss"]) / o["loss"] < TOL
+    assert relerr(dfeat.cpu().numpy(), o["dfeat"]) < TOL
+    assert relerr(dvecs.cpu().numpy(), o["dvecs"]) < TOL
+    assert relerr(dscale.cpu().numpy(), o["dscale"]) < TOL
+    assert abs(float(dbias) - o["dbias"]) / abs(o["dbias"]) < TOL
+    # and end to end against the pure-oracle loss (ties included): still within tolerance
+    o2 = O.synth_loss_and_grads("bce", feat, vecs, scale, bias, prep["gt_masks"], prep["weights"])
+    assert abs(float(loss) - o2["loss"]) / o2["loss"] < 1e-3
+    # host-buffer entry point gives the same numbers
+    wh = torch.from_numpy(waves).pin_memory()
+    vh = torch.from_numpy(vecs).pin_memory()
+    dfeat2 = torch.empty_like(dfeat)
+    dv_host = torch.empty((B, N, K)).pin_memory()
+    lh = st.train_host(wh, vh, tfeat, c(scale), c(bias), dfeat2, dv_host)
+    assert lh == float(loss) and torch.equal(dfeat, dfeat2) and torch.equal(dv_host.cuda(), dvecs)
+    st.close()
+
+
+def test_eval_step_vs_oracle_with_sdr():
+    B, N, K = 2, 2, 32
+    waves, feat, vecs, scale, bias = _inputs(B, N, K, seed=4321)
+    c = lambda a: torch.from_numpy(a).cuda()
+    # make the synthesizer emit useful masks: feat channel 0 carries the logit of the ideal mask of source 0
+    amp, prep = _oracle_front(waves, N, B)
+    feat[:] *= 0.05
+    logit = (prep["gt_masks"][0][:, 0] * 2 - 1) * 3.0
+    feat[:, 0] = logit
+    feat[:, 1] = -logit
+    vecs[:] = 0.0
+    vecs[:, 0, 0] = 1.0
+    vecs[:, 1, 1] = 1.0
+    scale[:] = 1.0
+    bias[:] = 0.0
+    st = av.Step(B, N, K, L)
+    wav = torch.empty((B, N + 1, 65280), device="cuda")
+    st.eval_dev(c(waves), c(vecs), c(feat), c(scale), c(bias), wav, binary_mask=True, mask_thres=0.5)
+    torch.cuda.synchronize()
+    pred = st.buffer("pred_masks").cpu().numpy()                 # [N,B,1,256,256]
+    z = [O.innerprod_forward(vecs[:, n], feat, scale, bias) for n in range(N)]
+    for n in range(N):
+        assert relerr(pred[n], O.sigmoid_f32(z[n].astype(np.float32))) < TOL
+    phase = np.stack([O.stft_magphase(waves[0, b])[1] for b in range(B)])[:, None]
+    mix_o, pred_o, _ = O.separate(amp[0][:, None], phase, [pred[n] for n in range(N)])
+    got = wav.cpu().numpy().astype(np.float64)
+    scale_w = np.max(np.abs(mix_o))
+    assert np.max(np.abs(got[:, 0] - mix_o)) / scale_w < TOL
+    for n in range(N):
+        assert np.max(np.abs(got[:, 1 + n] - pred_o[:, n])) / scale_w < TOL
+    # north-star criterion: per-clip SDR / SIR / SAR within 0.01 dB
+    for j in range(B):
+        gts = waves[1:, j, :65280].astype(np.float64)
+        m_gpu = BSS.get_metrics(got[j, 0], gts, got[j, 1:])
+        m_ref = BSS.get_metrics(mix_o[j], gts, pred_o[j])
+        for k in ("sdr", "sir", "sar", "si_sdr"):
+            assert abs(m_gpu[k] - m_ref[k]) < 0.01, (k, m_gpu[k], m_ref[k])
+        assert m_ref["sdr"] > 3.0                                 # the masks do separate
+    # host-buffer variant
+    wav_h = torch.empty((B, N + 1, 65280)).pin_memory()
+    st.eval_host(torch.from_numpy(waves).pin_memory(), torch.from_numpy(vecs).pin_memory(), c(feat), c(scale), c(bias), wav_h)
+    assert torch.equal(wav_h.cuda(), wav)
+    st.close()
+
+
+def test_calc_metrics_dropin_matches_reference_golden(golden):
+    """calc_metrics (main.py:197-286) with the masks the golden generator fed to the REAL reference function."""
+    g = golden("calc_metrics")
+    waves = O.synth_sources(2, 2, seed=77)
+    mixw = waves.sum(axis=1).astype(np.float32)
+    mag, ph = av.stft(torch.from_numpy(mixw).cuda())
+    pm = [torch.from_numpy(g[f"pred_mask{n}"].astype(np.float32)).cuda() for n in range(2)]
+    args = types.SimpleNamespace(num_mix=2, log_freq=1, stft_frame=1022, stft_hop=256, binary_mask=1, mask_thres=0.5)
+    batch = dict(mag_mix=mag[:, None].cpu(), phase_mix=ph[:, None].cpu(), audios=[torch.from_numpy(waves[:, n]) for n in range(2)])
+    gm = lambda mix, clean, est, sample_rate=None, metrics_list=None: BSS.get_metrics(mix, clean, est)
+    res = av.calc_metrics(batch, dict(pred_masks=pm), args, get_metrics=gm)
+    assert res[0] == 0 and len(res) == 8
+    assert np.max(np.abs(np.asarray(res[4]) - g["sdr"])) < 0.01
+    assert np.max(np.abs(np.asarray(res[5]) - g["sir"])) < 0.01
+    assert np.max(np.abs(np.asarray(res[6]) - g["si_sdr"])) < 0.01
+    assert abs(res[1] - float(g["sdr_avg"])) < 0.01 and abs(res[3] - float(g["sar_avg"])) < 0.01
+
+
+def test_n3_and_batch_shapes():
+    """Config C3 shape family (N = 3) at a small batch, plus B = 1 (config C1)."""
+    for B, N in ((1, 2), (3, 3)):
+        waves, feat, vecs, scale, bias = _inputs(B, N, 32, seed=99 + N)
+        c = lambda a: torch.from_numpy(a).cuda()
+        st = av.Step(B, N, 32, L)
+        wav = torch.empty((B, N + 1, 65280), device="cuda")
+        st.eval_dev(c(waves), c(vecs), c(feat), c(scale), c(bias), wav, binary_mask=False)
+        torch.cuda.synchronize()
+        pred = st.buffer("pred_masks").cpu().numpy()
+        amp = np.stack([O.stft_magphase(waves[0, b])[0] for b in range(B)])[:, None]
+        phase = np.stack([O.stft_magphase(waves[0, b])[1] for b in range(B)])[:, None]
+        mix_o, pred_o, _ = O.separate(amp, phase, [pred[n] for n in range(N)], binary_mask=False)
+        got = wav.cpu().numpy()
+        s = np.max(np.abs(mix_o))
+        assert np.max(np.abs(got[:, 0] - mix_o)) / s < TOL
+        for n in range(N):
+            assert np.max(np.abs(got[:, 1 + n] - pred_o[:, n])) / s < TOL
+        st.close()
