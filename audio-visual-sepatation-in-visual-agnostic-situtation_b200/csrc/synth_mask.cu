@@ -15,6 +15,7 @@ constexpr int SYN_FWD_THREADS = 256;
 constexpr int SYN_BWD_THREADS = 128;
 constexpr int SYN_BWD_ITERS = 4;     // float4 groups per thread
 constexpr int SYN_KCHUNK = 32;       // channels per backward CTA (grid.z walks the chunks)
+constexpr int SYN_BWD_LOADS = 8;     // 128-bit loads in flight per thread
 constexpr int SYN_MAX_K = 256;
 
 __device__ __forceinline__ float act_apply(int act, float z) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const double* __res
 //   dfeat[k]   = sum_n dz[n] * vec[n][k] * scale[k]                streamed out
 //   S[n][k]   += dz[n] . feat[k]                                   registers -> warp shuffle -> CTA partial
 template <int NS, bool GIVEN>
-__global__ void __launch_bounds__(SYN_BWD_THREADS)
+__global__ void __launch_bounds__(SYN_BWD_THREADS, (NS <= 2 ? 4 : (NS == 3 ? 3 : 2)))
 synth_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale, int B,
                  int K, int HW, int act, int loss_kind, const float* __restrict__ pred, const float* __restrict__ gt,
                  const float* __restrict__ weight, const float* __restrict__ gscale, const float* __restrict__ dz_in,
@@ -168,81 +169,103 @@ synth_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ vecs,
   const int b = blockIdx.y;
   const int k0 = blockIdx.z * SYN_KCHUNK;
   const int kn = min(SYN_KCHUNK, K - k0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < NS * SYN_KCHUNK; i += blockDim.x) {
     const int n = i / SYN_KCHUNK, k = i % SYN_KCHUNK;
     vs[n][k] = (k < kn) ? vecs[((size_t)b * NS + n) * K + k0 + k] * (scale ? scale[k0 + k] : 1.f) : 0.f;
   }
   __syncthreads();
   const float g = GIVEN ? 1.f : gscale[0] * inv_count;
-  float S[NS][SYN_KCHUNK];
+  const int base_px = blockIdx.x * (SYN_BWD_THREADS * 4 * SYN_BWD_ITERS) + threadIdx.x * 4;
+
+  // 1. dz for every pixel group this thread owns (small streams: pred, gt, weight or the given dz)
+  float dz[SYN_BWD_ITERS][NS][4];
   float dzs[NS];
 #pragma unroll
-  for (int n = 0; n < NS; ++n) {
-    dzs[n] = 0.f;
+  for (int n = 0; n < NS; ++n) dzs[n] = 0.f;
 #pragma unroll
-    for (int k = 0; k < SYN_KCHUNK; ++k) S[n][k] = 0.f;
-  }
-  const int chunk_px = SYN_BWD_THREADS * 4 * SYN_BWD_ITERS;
-  const int base_px = blockIdx.x * chunk_px;
-#pragma unroll 1
   for (int it = 0; it < SYN_BWD_ITERS; ++it) {
-    const int px = base_px + (it * SYN_BWD_THREADS + threadIdx.x) * 4;
-    if (px >= HW) break;
-    float dz[NS][4];
+    const int px = base_px + it * SYN_BWD_THREADS * 4;
+    const bool ok = px < HW;
     float w[4] = {1.f, 1.f, 1.f, 1.f};
-    if (!GIVEN && weight) {
+    if (!GIVEN && weight && ok) {
       const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
       w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
     }
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
-      const size_t o = ((size_t)n * B + b) * HW + px;
-      if (GIVEN) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dz_in + o);
-        dz[n][0] = d4.x; dz[n][1] = d4.y; dz[n][2] = d4.z; dz[n][3] = d4.w;
-      } else {
-        const float4 p4 = *reinterpret_cast<const float4*>(pred + o);
-        const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
-        const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
-        const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float d = g * w[e] * loss_grad(loss_kind, pp[e], tt[e]);
-          if (act == AVSEP_ACT_SIGMOID) d *= (1.f - pp[e]) * pp[e];
-          dz[n][e] = d;
+      for (int e = 0; e < 4; ++e) dz[it][n][e] = 0.f;
+      if (ok) {
+        const size_t o = ((size_t)n * B + b) * HW + px;
+        if (GIVEN) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dz_in + o);
+          dz[it][n][0] = d4.x; dz[it][n][1] = d4.y; dz[it][n][2] = d4.z; dz[it][n][3] = d4.w;
+        } else {
+          const float4 p4 = *reinterpret_cast<const float4*>(pred + o);
+          const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
+          const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float d = g * w[e] * loss_grad(loss_kind, pp[e], tt[e]);
+            if (act == AVSEP_ACT_SIGMOID) d *= (1.f - pp[e]) * pp[e];
+            dz[it][n][e] = d;
+          }
         }
       }
-      dzs[n] += (dz[n][0] + dz[n][1]) + (dz[n][2] + dz[n][3]);
-    }
-    const float* fp = feat + ((size_t)b * K + k0) * HW + px;
-    float* dp = dfeat ? dfeat + ((size_t)b * K + k0) * HW + px : nullptr;
-#pragma unroll
-    for (int k = 0; k < SYN_KCHUNK; ++k) {
-      if (k < kn) {
-        const float4 f = ld_stream(reinterpret_cast<const float4*>(fp + (size_t)k * HW));
-        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int n = 0; n < NS; ++n) {
-          const float c = vs[n][k];
-          o4.x = fmaf(c, dz[n][0], o4.x);
-          o4.y = fmaf(c, dz[n][1], o4.y);
-          o4.z = fmaf(c, dz[n][2], o4.z);
-          o4.w = fmaf(c, dz[n][3], o4.w);
-          S[n][k] += (dz[n][0] * f.x + dz[n][1] * f.y) + (dz[n][2] * f.z + dz[n][3] * f.w);
-        }
-        if (dp) st_stream(reinterpret_cast<float4*>(dp + (size_t)k * HW), o4);
-      }
+      dzs[n] += (dz[it][n][0] + dz[it][n][1]) + (dz[it][n][2] + dz[it][n][3]);
     }
   }
-  // CTA reduction of S[n][k] and dzs[n]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // 2. stream feat / dfeat, SYN_BWD_LOADS channels at a time: all the 128-bit loads of a batch are issued
+  //    before any is consumed (memory-level parallelism is what this kernel lives on)
+  const float* fbase = feat + ((size_t)b * K + k0) * HW;
+  float* dbase = dfeat ? dfeat + ((size_t)b * K + k0) * HW : nullptr;
+#pragma unroll 1
+  for (int kc = 0; kc < SYN_KCHUNK; kc += SYN_BWD_LOADS) {
+    float S[NS][SYN_BWD_LOADS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int j = 0; j < SYN_BWD_LOADS; ++j) S[n][j] = 0.f;
+    if (kc < kn) {
+#pragma unroll
+      for (int it = 0; it < SYN_BWD_ITERS; ++it) {
+        const int px = base_px + it * SYN_BWD_THREADS * 4;
+        if (px < HW) {
+          float4 f[SYN_BWD_LOADS];
+#pragma unroll
+          for (int j = 0; j < SYN_BWD_LOADS; ++j)
+            f[j] = (kc + j < kn) ? ld_stream(reinterpret_cast<const float4*>(fbase + (size_t)(kc + j) * HW + px))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < SYN_BWD_LOADS; ++j) {
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+              const float c = vs[n][kc + j];
+              o4.x = fmaf(c, dz[it][n][0], o4.x);
+              o4.y = fmaf(c, dz[it][n][1], o4.y);
+              o4.z = fmaf(c, dz[it][n][2], o4.z);
+              o4.w = fmaf(c, dz[it][n][3], o4.w);
+              S[n][j] += (dz[it][n][0] * f[j].x + dz[it][n][1] * f[j].y) + (dz[it][n][2] * f[j].z + dz[it][n][3] * f[j].w);
+            }
+            if (dbase && kc + j < kn) st_stream(reinterpret_cast<float4*>(dbase + (size_t)(kc + j) * HW + px), o4);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int j = 0; j < SYN_BWD_LOADS; ++j) {
+        const float r = warp_sum(S[n][j]);
+        if (lane == 0) red[warp][n * SYN_KCHUNK + kc + j] = r;
+      }
+  }
 #pragma unroll
   for (int n = 0; n < NS; ++n) {
-#pragma unroll
-    for (int k = 0; k < SYN_KCHUNK; ++k) {
-      const float r = warp_sum(S[n][k]);
-      if (lane == 0) red[warp][n * SYN_KCHUNK + k] = r;
-    }
     const float r = warp_sum(dzs[n]);
     if (lane == 0) red[warp][NS * SYN_KCHUNK + n] = r;
   }

@@ -60,7 +60,9 @@ def test_warp_equals_torch_grid_sample_on_gpu():
     for T in (1, 7, 250, 300):
         x = torch.rand((2, 1, 512, T), device="cuda")
         grid = torch.from_numpy(av.warpgrid(2, 256, T, warp=True)).cuda()
-        assert float((av.warp(x, 256, True) - F.grid_sample(x, grid, align_corners=False)).abs().max()) < 2e-6
+        # non-power-of-two widths: ATen's GPU kernel contracts ((g + 1) * W - 1) / 2 into FMAs, the host-side tap
+        # table (and ATen's CPU kernel) does not, so the two "reference" paths differ by an ulp of the coordinate
+        assert float((av.warp(x, 256, True) - F.grid_sample(x, grid, align_corners=False)).abs().max()) < 2e-5
 
 
 @pytest.mark.parametrize("binary,weighted", [(True, True), (False, False)])
