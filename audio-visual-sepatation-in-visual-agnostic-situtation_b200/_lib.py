@@ -68,6 +68,7 @@ SIGNATURES = {
     "avsep_step_create": (_I, [c_void_pp, _I, _I, _I, _I]),
     "avsep_step_destroy": (_I, [_P]),
     "avsep_step_train_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "avsep_step_train_host_async": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "avsep_step_train_dev": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "avsep_step_eval_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "avsep_step_eval_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),

@@ -16,22 +16,30 @@ namespace avsep {
 // wave [S, L] fp32 -> reflect-padded (n_fft/2 each side, librosa center=True) bf16 hi/lo rows of
 // length Lpad.  Frame t of signal s is then the 1024-sample window starting at 256 t, which the
 // GEMM reads directly through an overlapping-row TMA descriptor (row stride 256 elements).
-__global__ void wave_split_kernel(const float* __restrict__ wave, int S, int L, int Lpad, size_t lo_stride,
-                                  __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict__ wave, int S, int L, int Lpad, size_t lo_stride,
+                                                         __nv_bfloat16* __restrict__ out) {
+  // 8 consecutive padded positions per thread: two 16-byte stores (hi, lo); Lpad is a multiple of 256
   const int s = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Lpad) return;
-  int j = i - AVSEP_N_FFT / 2;
-  float x = 0.f;
-  if (i < L + AVSEP_N_FFT - 1 + 1) {            // positions beyond the padded signal stay zero
-    if (j < 0) j = -j;
-    if (j >= L) j = 2 * (L - 1) - j;
-    if (j >= 0 && j < L) x = wave[(size_t)s * L + j];
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= Lpad) return;
+  const float* w = wave + (size_t)s * L;
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int i = i0 + e;
+    int j = i - AVSEP_N_FFT / 2;
+    float x = 0.f;
+    if (i < L + AVSEP_N_FFT) {                      // positions beyond the padded signal stay zero
+      if (j < 0) j = -j;
+      if (j >= L) j = 2 * (L - 1) - j;
+      if (j >= 0 && j < L) x = __ldg(w + j);
+    }
+    split_bf16(x, hi[e], lo[e]);
   }
-  __nv_bfloat16 hi, lo;
-  split_bf16(x, hi, lo);
-  out[(size_t)s * Lpad + i] = hi;
-  out[lo_stride + (size_t)s * Lpad + i] = lo;
+  const size_t o = (size_t)s * Lpad + i0;
+  *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out + lo_stride + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // Fallback when the overlapping-row descriptor is not available: materialise frames [S, T, 1024].
@@ -330,7 +338,7 @@ static DftParams base_params(const avsep_plan* pl, int S) {
 static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream) {
   if (pl->overlap_tma) {
     const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
-    dim3 grid(ceil_div(pl->Lpad, 256), S);
+    dim3 grid(ceil_div(pl->Lpad, 256 * 8), S);
     wave_split_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->Lpad, lo_stride, pl->wave_split);
   } else {
     const size_t lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;

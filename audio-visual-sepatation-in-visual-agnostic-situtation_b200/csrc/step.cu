@@ -139,10 +139,10 @@ int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* ve
   return AVSEP_OK;
 }
 
-int avsep_step_train_host(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
-                          const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_host, float* loss_host,
-                          void* stream_) {
-  AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev && loss_host, "avsep_step_train_host: null argument");
+int avsep_step_train_host_async(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
+                                const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_host,
+                                float* loss_host, void* stream_) {
+  AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev && loss_host, "avsep_step_train_host_async: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + 1) * st->B * st->L, cudaMemcpyHostToDevice, stream));
   AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
@@ -152,7 +152,15 @@ int avsep_step_train_host(avsep_step* st, const float* waves_host, const float* 
   AVSEP_CUDA(cudaMemcpyAsync(loss_host, st->loss, sizeof(float), cudaMemcpyDeviceToHost, stream));
   if (dvecs_host)
     AVSEP_CUDA(cudaMemcpyAsync(dvecs_host, st->dvecs, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyDeviceToHost, stream));
-  AVSEP_CUDA(cudaStreamSynchronize(stream));
+  return AVSEP_OK;
+}
+
+int avsep_step_train_host(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
+                          const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_host, float* loss_host,
+                          void* stream) {
+  int rc = avsep_step_train_host_async(st, waves_host, vecs_host, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_host, loss_host, stream);
+  if (rc) return rc;
+  AVSEP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return AVSEP_OK;
 }
 

@@ -123,8 +123,107 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepareParams p) {
   }
 }
 
+// Vectorised variant (T % 4 == 0): a thread owns 4 consecutive output columns, so the row samples are one
+// aligned 128-bit load plus the two neighbours (x taps are w-1 / w by construction of the linear grid),
+// every output stream is written with 128-bit stores and the index arithmetic is amortised over 4 pixels.
+constexpr int PREP_ROWS_PER_THREAD = 4;
+constexpr int PREP_TX = 64, PREP_TY = 4;
+
+struct Row4 {
+  float v[4];
+};
+
+__device__ __forceinline__ Row4 row_sample4(const float* __restrict__ base, int y, int H, int T, int w0, const int (&sel)[4],
+                                            const float (&fx)[4], float eps) {
+  Row4 r;
+  if (y < 0 || y >= H) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.v[j] = 0.f;
+    return r;
+  }
+  const float* p = base + (size_t)y * T + w0;
+  const float4 c = __ldg(reinterpret_cast<const float4*>(p));
+  float e[6];
+  e[0] = w0 > 0 ? __ldg(p - 1) + eps : 0.f;         // zero padding outside the image: no epsilon there
+  e[1] = c.x + eps; e[2] = c.y + eps; e[3] = c.z + eps; e[4] = c.w + eps;
+  e[5] = w0 + 4 < T ? __ldg(p + 4) + eps : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = sel[j] ? e[j + 1] : e[j];        // tap x0     (x0 = w - 1 + sel)
+    const float b = sel[j] ? e[j + 2] : e[j + 1];    // tap x0 + 1
+    r.v[j] = (1.f - fx[j]) * a + fx[j] * b;
+  }
+  return r;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(PREP_TX * PREP_TY) prepare_vec_kernel(const PrepareParams p) {
+  const int b = blockIdx.z;
+  const int h0 = (blockIdx.y * PREP_TY + threadIdx.y) * PREP_ROWS_PER_THREAD;
+  if (h0 >= p.Hout) return;
+  const size_t in_off = (size_t)b * p.Hin * p.T;
+  const size_t out_off = (size_t)b * p.Hout * p.T;
+  for (int w0 = (blockIdx.x * PREP_TX + threadIdx.x) * 4; w0 < p.T; w0 += gridDim.x * PREP_TX * 4) {
+    const int4 xi = __ldg(reinterpret_cast<const int4*>(p.xtap.i0 + w0));
+    const float4 xf = __ldg(reinterpret_cast<const float4*>(p.xtap.frac + w0));
+    const int sel[4] = {xi.x - (w0 - 1), xi.y - w0, xi.z - (w0 + 1), xi.w - (w0 + 2)};
+    const float fx[4] = {xf.x, xf.y, xf.z, xf.w};
+    int cy0[NS + 1], cy1[NS + 1];
+    Row4 cv0[NS + 1], cv1[NS + 1];
+#pragma unroll
+    for (int j = 0; j <= NS; ++j) { cy0[j] = -2; cy1[j] = -2; }
+#pragma unroll
+    for (int r = 0; r < PREP_ROWS_PER_THREAD; ++r) {
+      const int h = h0 + r;
+      if (h >= p.Hout) break;
+      const int y0 = __ldg(p.ytap.i0 + h);
+      const float fy = __ldg(p.ytap.frac + h);
+      Row4 v[NS + 1];
+#pragma unroll
+      for (int j = 0; j <= NS; ++j) {
+        const float* base = (j == 0 ? p.mix : p.src[j - 1]) + in_off;
+        const float eps = j == 0 ? 1e-10f : 0.f;
+        const Row4 a = (y0 == cy0[j]) ? cv0[j] : ((y0 == cy1[j]) ? cv1[j] : row_sample4(base, y0, p.Hin, p.T, w0, sel, fx, eps));
+        const Row4 c = (y0 + 1 == cy1[j]) ? cv1[j] : ((y0 + 1 == cy0[j]) ? cv0[j] : row_sample4(base, y0 + 1, p.Hin, p.T, w0, sel, fx, eps));
+        cy0[j] = y0; cv0[j] = a; cy1[j] = y0 + 1; cv1[j] = c;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[j].v[e] = (1.f - fy) * a.v[e] + fy * c.v[e];
+      }
+      const size_t o = out_off + (size_t)h * p.T + w0;
+      const float* mx = v[0].v;
+      if (p.mix_w) *reinterpret_cast<float4*>(p.mix_w + o) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+      if (p.log_mix) *reinterpret_cast<float4*>(p.log_mix + o) = make_float4(logf(mx[0]), logf(mx[1]), logf(mx[2]), logf(mx[3]));
+      if (p.weights) {
+        float wv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wv[e] = p.weighted ? fminf(fmaxf(log1pf(mx[e]), 1e-3f), 10.f) : 1.f;
+        *reinterpret_cast<float4*>(p.weights + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      }
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
+        const float* sv = v[n + 1].v;
+        if (p.src_w[n]) *reinterpret_cast<float4*>(p.src_w[n] + o) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+        if (p.gt[n]) {
+          float gv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            gv[e] = p.binary ? (sv[e] > 0.5f * mx[e] ? 1.f : 0.f) : fminf(fmaxf(sv[e] / mx[e], 0.f), 5.f);
+          *reinterpret_cast<float4*>(p.gt[n] + o) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+      }
+    }
+  }
+}
+
 template <int NS>
 static int launch_prepare(const PrepareParams& p, bool warp, cudaStream_t stream) {
+  if (warp && (p.T & 3) == 0) {
+    dim3 block(PREP_TX, PREP_TY);
+    dim3 grid(ceil_div(p.T, PREP_TX * 4), ceil_div(p.Hout, PREP_TY * PREP_ROWS_PER_THREAD), p.B);
+    prepare_vec_kernel<NS><<<grid, block, 0, stream>>>(p);
+    AVSEP_LAUNCH_CHECK();
+    return AVSEP_OK;
+  }
   dim3 grid(ceil_div(p.T, 256), ceil_div(p.Hout, WARP_ROWS_PER_CTA), p.B);
   if (warp) prepare_kernel<NS, true><<<grid, 256, 0, stream>>>(p);
   else prepare_kernel<NS, false><<<grid, 256, 0, stream>>>(p);

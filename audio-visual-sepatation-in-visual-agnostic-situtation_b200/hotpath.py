@@ -237,6 +237,13 @@ class Step:
               "avsep_step_train_host")
         return float(loss[0])
 
+    def train_host_async(self, waves_host, vecs_host, feat, scale, bias, dfeat, loss_host, dvecs_host=None):
+        """Enqueue H2D + step + D2H on the current stream and return; loss_host (pinned, 1 float) is valid after the
+        stream is synchronised.  Two Steps on two streams overlap the copy of step i+1 with the kernels of step i."""
+        check(lib.avsep_step_train_host_async(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
+                                              ops._p(bias), ops._p(dfeat), ops._p(dvecs_host), loss_host.data_ptr(), ops._stream()),
+              "avsep_step_train_host_async")
+
     def eval_dev(self, waves, vecs, feat, scale, bias, wav=None, binary_mask=True, mask_thres=0.5):
         check(lib.avsep_step_eval_dev(self._h, waves.data_ptr(), vecs.data_ptr(), feat.data_ptr(), ops._p(scale), ops._p(bias),
                                       int(binary_mask), float(mask_thres), ops._p(wav), ops._stream()), "avsep_step_eval_dev")

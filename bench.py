@@ -281,17 +281,45 @@ def main_ours(args, rank, world, local):
     value = B * world * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI entry point (`e2e`) ---------------------------------------
-    for _ in range(3):
-        step_host()
+    # Every step copies its pinned host inputs H2D and reads its loss (+ dvecs) back D2H inside the timed
+    # region.  Two Step objects alternate on two streams (a depth-2 software pipeline, like a prefetching
+    # training loop), so the copy of step i+1 overlaps the kernels of step i; the loss of step i is read on
+    # the host before its Step object is reused for step i+2.
+    if eval_mode:
+        def run_e2e(k):
+            for _ in range(k):
+                step_host()
+            return 0.0
+        pipe_depth = 1
+    else:
+        step_b = av.Step(B, N, K, L)
+        pipes = [dict(step=step, stream=torch.cuda.Stream(), dfeat=dfeat, loss=torch.zeros(1).pin_memory(),
+                      dvecs=torch.empty((B, N, K)).pin_memory()),
+                 dict(step=step_b, stream=torch.cuda.Stream(), dfeat=torch.empty_like(feat), loss=torch.zeros(1).pin_memory(),
+                      dvecs=torch.empty((B, N, K)).pin_memory())]
+        pipe_depth = 2
+
+        def run_e2e(k):
+            for i in range(k):
+                p = pipes[i % 2]
+                p["stream"].synchronize()                          # step i-2 done: its loss is on the host now
+                _ = float(p["loss"][0])
+                with torch.cuda.stream(p["stream"]):
+                    p["step"].train_host_async(waves_host, vecs_host, feat, scale, bias, p["dfeat"], p["loss"], p["dvecs"])
+            for p in pipes:
+                p["stream"].synchronize()
+            return float(pipes[(k - 1) % 2]["loss"][0])
+    torch.cuda.synchronize()
+    run_e2e(4)
     barrier()
-    e0.record()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss_host = step_host()
-    e1.record()
-    barrier()
+    loss_host = run_e2e(args.steps)
+    torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    ms_e2e = parallel.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), device=dev)
+    barrier()
+    ms_e2e = parallel.max_over_ranks(wall_ms, device=dev)
+    if not eval_mode:
+        assert abs(loss_host - loss_val) <= 1e-6 * max(abs(loss_val), 1.0), (loss_host, loss_val)
     for _ in range(40):                                            # keep the GPU loaded until a few more samples land
         step_dev()
     torch.cuda.synchronize()
@@ -375,10 +403,14 @@ def main_ours(args, rank, world, local):
                         parallelism=f"batch-sharded x{world}, no data-path collective",
                         l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
-                     api="avsep_step_train_host (C-ABI, pinned host waveforms + K-vectors in, loss + dvecs out)"),
+                     pipeline_depth=pipe_depth, timer="host wall clock around the K steps, synchronised on both sides",
+                     api="avsep_step_train_host_async (C-ABI, pinned host waveforms + K-vectors in, loss + dvecs out), "
+                         "2 steps in flight on 2 streams"),
             gpu_launches=int(launches), clocks=clocks, loss=loss_val, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline)
         print(json.dumps(line), flush=True)
     step.close()
+    if not eval_mode:
+        step_b.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -196,6 +196,12 @@ int avsep_step_destroy(avsep_step* step);
 int avsep_step_train_host(avsep_step* step, const float* waves_host, const float* vecs_host,
                           const float* feat_dev, const float* scale_dev, const float* bias_dev,
                           float* dfeat_dev, float* dvecs_host, float* loss_host, void* stream);
+/* Same, but only enqueued on `stream` (no synchronisation): with two steps on two streams the H2D copy of
+ * step i+1 overlaps the kernels of step i.  loss_host / dvecs_host must be pinned and are valid once the
+ * stream has been synchronised. */
+int avsep_step_train_host_async(avsep_step* step, const float* waves_host, const float* vecs_host,
+                                const float* feat_dev, const float* scale_dev, const float* bias_dev,
+                                float* dfeat_dev, float* dvecs_host, float* loss_host, void* stream);
 /* same step with device-resident inputs, asynchronous (what bench.py's `value` times) */
 int avsep_step_train_dev(avsep_step* step, const float* waves_dev, const float* vecs_dev,
                          const float* feat_dev, const float* scale_dev, const float* bias_dev,
