@@ -83,7 +83,8 @@ def make_waves(B, N, seed):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -95,9 +96,15 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def lines(self):
+        try:
+            return sum(1 for r in open(self.path) if r.strip())
+        except Exception:
+            return 0
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
@@ -110,12 +117,16 @@ class ClockSampler:
             self.proc.kill()
         try:
             rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            rows = [r for r in rows if len(r) >= 10]
+            loaded = [r for r in rows if float(r[9]) >= 50.0] or rows       # samples taken while the GPU was busy
+            total = len(rows)
+            rows = loaded
             sm = [float(r[1]) for r in rows]
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")})
             if sm:
-                out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(rows[0][2]), reasons=reasons, samples=len(sm),
-                           power_w_max=max(float(r[3]) for r in rows))
+                out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(rows[0][2]), reasons=reasons, samples=total,
+                           samples_under_load=len(sm), power_w_max=max(float(r[3]) for r in rows))
         except Exception:
             pass
         finally:
@@ -254,18 +265,22 @@ def main_ours(args, rank, world, local):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`) ------------------------------------------------------------
-    # The clock sampler runs from before the warm-up to after the e2e loop, so its samples bracket both timed
-    # regions; the warm-up is stretched to >= 0.6 s of load because nvidia-smi needs ~100 ms per sample.
+    # The clock sampler (nvidia-smi -lms 200) runs from before the warm-up to after the e2e loop so its samples
+    # bracket both timed regions.  Its start-up (NVML attach) perturbs kernel launches for a few hundred ms, so the
+    # warm-up keeps the GPU loaded until the sampler has produced its first samples (bounded at 4 s).
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     t_w = time.perf_counter()
     n_w = 0
-    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 0.6:
+    while True:
         step_dev()
         n_w += 1
         if n_w % 8 == 0:
             torch.cuda.synchronize()
+            el = time.perf_counter() - t_w
+            if n_w >= max(args.warmup, 3) and (rank != 0 or sampler.proc is None or sampler.lines() >= 3 or el > 4.0) and el > 0.3:
+                break
     barrier()
     launches0 = av.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
