@@ -74,6 +74,7 @@ SIGNATURES = {
     "avsep_step_eval_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "avsep_step_buffer": (_P, [_P, _I]),
     "avsep_step_plan": (_P, [_P]),
+    "avsep_step_set_mix_on_device": (_I, [_P, _I]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -209,7 +209,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u)) << 61;
+  d |= (uint64_t)(row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u)) << 61;   // 6 = SWIZZLE_32B
   return d;
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M x N

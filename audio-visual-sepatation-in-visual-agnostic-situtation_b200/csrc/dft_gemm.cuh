@@ -32,17 +32,21 @@ constexpr int DFT_SCRATCH_BYTES = 2 * 4 * 32 * 32 * 4;   // inverse epilogue ove
 
 enum DftEpilogue : int { EPI_STFT = 0, EPI_ISTFT = 1, EPI_RAW = 2 };
 
-template <int BK>
+constexpr int DFT_SMEM_LIMIT = 232448;   // 227 KB opt-in shared memory per CTA on sm_100
+
+template <int BK, int EPI>
 struct DftCfg {
-  static_assert(BK == 32 || BK == 64, "K block is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
+  static_assert(BK == 16 || BK == 32 || BK == 64, "K block is 16 (SWIZZLE_32B), 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
   static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int STAGES = (BK == 64) ? 2 : 4;
   static constexpr int A_BYTES = DFT_TILE_M * ROW_BYTES;     // one split of the basis tile
   static constexpr int B_BYTES = DFT_TILE_N * ROW_BYTES;     // one split of the signal tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SCRATCH_BYTES = (EPI == 1) ? DFT_SCRATCH_BYTES : 0;   // only the inverse epilogue exchanges through smem
+  static constexpr int STAGES = (DFT_SMEM_LIMIT - 1024 - 256 - SCRATCH_BYTES) / STAGE_BYTES;   // 9/8, 4, 2
   static constexpr int K_BLOCKS = DFT_K / BK;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + DFT_SCRATCH_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + SCRATCH_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers/tmem slot + alignment slack
+  static_assert(STAGES >= 2 && (2 * STAGES + 5) * 8 <= 256, "barrier block overflow");
 };
 
 struct DftParams {
@@ -69,7 +73,7 @@ struct DftParams {
 template <int BK, int EPI>
 __global__ void __launch_bounds__(DFT_THREADS, 1)
 dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DftParams p) {
-  using Cfg = DftCfg<BK>;
+  using Cfg = DftCfg<BK, EPI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));

@@ -16,13 +16,17 @@ namespace avsep {
 // wave [S, L] fp32 -> reflect-padded (n_fft/2 each side, librosa center=True) bf16 hi/lo rows of
 // length Lpad.  Frame t of signal s is then the 1024-sample window starting at 256 t, which the
 // GEMM reads directly through an overlapping-row TMA descriptor (row stride 256 elements).
+// mix_N > 0: `wave` holds only the N sources [N, mix_B, L]; signals s < mix_B are the mixtures, formed here as
+// the sum of their sources (dataset/music.py:127), signals s >= mix_B are the sources themselves.
 __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict__ wave, int S, int L, int Lpad, size_t lo_stride,
-                                                         __nv_bfloat16* __restrict__ out) {
+                                                         __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
   // 8 consecutive padded positions per thread: two 16-byte stores (hi, lo); Lpad is a multiple of 256
   const int s = blockIdx.y;
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i0 >= Lpad) return;
-  const float* w = wave + (size_t)s * L;
+  const bool is_mix = mix_N > 0 && s < mix_B;
+  const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
+  const size_t src_stride = (size_t)mix_B * L;
   __align__(16) __nv_bfloat16 hi[8];
   __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
@@ -33,7 +37,11 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict
     if (i < L + AVSEP_N_FFT) {                      // positions beyond the padded signal stay zero
       if (j < 0) j = -j;
       if (j >= L) j = 2 * (L - 1) - j;
-      if (j >= 0 && j < L) x = __ldg(w + j);
+      if (j >= 0 && j < L) {
+        x = __ldg(w + j);
+        if (is_mix)
+          for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
+      }
     }
     split_bf16(x, hi[e], lo[e]);
   }
@@ -44,16 +52,23 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict
 
 // Fallback when the overlapping-row descriptor is not available: materialise frames [S, T, 1024].
 __global__ void wave_frames_kernel(const float* __restrict__ wave, int S, int L, int T, size_t lo_stride,
-                                   __nv_bfloat16* __restrict__ out) {
+                                   __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
   const int st = blockIdx.x;            // s * T + t
   const int s = st / T, t = st % T;
+  const bool is_mix = mix_N > 0 && s < mix_B;
+  const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
+  const size_t src_stride = (size_t)mix_B * L;
   for (int k = threadIdx.x; k < DFT_K; k += blockDim.x) {
     int j = t * AVSEP_HOP + k - AVSEP_N_FFT / 2;
     float x = 0.f;
     if (k < AVSEP_N_FFT) {
       if (j < 0) j = -j;
       if (j >= L) j = 2 * (L - 1) - j;
-      if (j >= 0 && j < L) x = wave[(size_t)s * L + j];
+      if (j >= 0 && j < L) {
+        x = w[j];
+        if (is_mix)
+          for (int n = 1; n < mix_N; ++n) x += w[n * src_stride + j];
+      }
     }
     __nv_bfloat16 hi, lo;
     split_bf16(x, hi, lo);
@@ -220,7 +235,7 @@ static int encode_map(CUtensorMap* tm, void* base, int rank, const cuuint64_t* d
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  kblock == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  kblock == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kblock == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(AVSEP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return AVSEP_OK;
@@ -310,12 +325,16 @@ static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap
   if (grid <= 0) return AVSEP_OK;
   if (pl->kblock == 64) {
     auto kern = dft_gemm_kernel<64, EPI>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<64>::SMEM_BYTES));
-    kern<<<grid, DFT_THREADS, DftCfg<64>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<64, EPI>::SMEM_BYTES));
+    kern<<<grid, DFT_THREADS, DftCfg<64, EPI>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  } else if (pl->kblock == 16) {
+    auto kern = dft_gemm_kernel<16, EPI>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<16, EPI>::SMEM_BYTES));
+    kern<<<grid, DFT_THREADS, DftCfg<16, EPI>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
   } else {
     auto kern = dft_gemm_kernel<32, EPI>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<32>::SMEM_BYTES));
-    kern<<<grid, DFT_THREADS, DftCfg<32>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<32, EPI>::SMEM_BYTES));
+    kern<<<grid, DFT_THREADS, DftCfg<32, EPI>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
   }
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
@@ -335,14 +354,14 @@ static DftParams base_params(const avsep_plan* pl, int S) {
   return prm;
 }
 
-static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream) {
+static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B = 0, int mix_N = 0) {
   if (pl->overlap_tma) {
     const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
     dim3 grid(ceil_div(pl->Lpad, 256 * 8), S);
-    wave_split_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->Lpad, lo_stride, pl->wave_split);
+    wave_split_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->Lpad, lo_stride, pl->wave_split, mix_B, mix_N);
   } else {
     const size_t lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
-    wave_frames_kernel<<<S * pl->T, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, lo_stride, pl->wave_split);
+    wave_frames_kernel<<<S * pl->T, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, lo_stride, pl->wave_split, mix_B, mix_N);
   }
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
@@ -378,7 +397,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
   pl->Lpad = AVSEP_HOP * (pl->T + 4);
   pl->out_len = AVSEP_HOP * (pl->T - 1);
   const char* env_bk = getenv("AVSEP_DFT_KBLOCK");
-  pl->kblock = (env_bk && atoi(env_bk) == 64) ? 64 : 32;
+  pl->kblock = env_bk ? atoi(env_bk) : 32;
+  if (pl->kblock != 16 && pl->kblock != 32 && pl->kblock != 64) pl->kblock = 32;
   const char* env_ov = getenv("AVSEP_DFT_NO_OVERLAP_TMA");
   pl->overlap_tma = !(env_ov && atoi(env_ov) != 0);
 
@@ -459,7 +479,7 @@ size_t avsep_plan_workspace_bytes(const avsep_plan* pl) { return pl ? pl->worksp
 
 int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_kblock: plan is null");
-  AVSEP_REQUIRE(kblock == 32 || kblock == 64, "avsep_plan_set_kblock: kblock must be 32 or 64 (got %d)", kblock);
+  AVSEP_REQUIRE(kblock == 16 || kblock == 32 || kblock == 64, "avsep_plan_set_kblock: kblock must be 16, 32 or 64 (got %d)", kblock);
   AVSEP_CUDA(cudaDeviceSynchronize());
   pl->kblock = kblock;
   return build_maps(pl);
@@ -469,14 +489,14 @@ int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
 
 namespace avsep {
 int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
-              int reim_count, void* stream_) {
+              int reim_count, void* stream_, int mix_B, int mix_N) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_stft: plan is null");
   AVSEP_REQUIRE(wave_dev && mag_dev, "avsep_stft: wave_dev and mag_dev are required");
   AVSEP_REQUIRE((re_dev == nullptr) == (im_dev == nullptr), "avsep_stft: re_dev and im_dev must be given together");
   AVSEP_REQUIRE(S >= 0 && S <= pl->max_signals, "avsep_stft: S = %d exceeds the plan capacity %d", S, pl->max_signals);
   if (S == 0) return AVSEP_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = stage_waves(pl, wave_dev, S, stream);
+  int rc = stage_waves(pl, wave_dev, S, stream, mix_B, mix_N);
   if (rc) return rc;
   DftParams prm = base_params(pl, S);
   prm.mag = mag_dev;
@@ -492,7 +512,7 @@ extern "C" {
 
 int avsep_stft(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev,
                float* im_dev, void* stream) {
-  return stft_impl(pl, wave_dev, S, mag_dev, phase_dev, re_dev, im_dev, S, stream);
+  return stft_impl(pl, wave_dev, S, mag_dev, phase_dev, re_dev, im_dev, S, stream, 0, 0);
 }
 
 int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const float* mag_dev, const float* phase_dev,

@@ -18,7 +18,7 @@ int synth_forward_impl(const float* feat, const float* vecs, const float* scale,
                        int act, float* out, int loss_kind, const float* gt, const float* weight, float* loss, void* scratch,
                        cudaStream_t stream);
 int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
-              int reim_count, void* stream);
+              int reim_count, void* stream, int mix_B, int mix_N);
 int synth_backward_impl(const float* feat, const float* vecs, const float* scale, int B, int N, int K, int HW, int act,
                         int loss_kind, const float* pred, const float* gt, const float* weight, const float* gscale,
                         const float* dz, float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch,
@@ -27,6 +27,7 @@ int synth_backward_impl(const float* feat, const float* vecs, const float* scale
 
 struct avsep_step {
   int B = 0, N = 0, K = 0, L = 0, T = 0, HW = 0, out_len = 0;
+  int mix_on_device = 0;      // waves arguments hold only the N sources; the mixture is summed on the GPU
   avsep_plan* plan = nullptr;
   float* waves = nullptr;     // [N+1, B, L]  (index 0 = mixture)
   float* vecs = nullptr;      // [B, N, K]
@@ -54,7 +55,7 @@ static int step_forward_common(avsep_step* st, const float* waves_dev, const flo
                                const float* scale_dev, const float* bias_dev, bool need_reim, cudaStream_t stream) {
   const int B = st->B, N = st->N;
   int rc = stft_impl(st->plan, waves_dev, (N + 1) * B, st->mag, nullptr, need_reim ? st->mix_re : nullptr,
-                     need_reim ? st->mix_im : nullptr, B, stream);
+                     need_reim ? st->mix_im : nullptr, B, stream, st->mix_on_device ? B : 0, st->mix_on_device ? N : 0);
   if (rc) return rc;
   const size_t sig = (size_t)AVSEP_N_BINS * st->T;
   const size_t img = (size_t)st->HW;
@@ -144,7 +145,7 @@ int avsep_step_train_host_async(avsep_step* st, const float* waves_host, const f
                                 float* loss_host, void* stream_) {
   AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev && loss_host, "avsep_step_train_host_async: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + 1) * st->B * st->L, cudaMemcpyHostToDevice, stream));
+  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + (st->mix_on_device ? 0 : 1)) * st->B * st->L, cudaMemcpyHostToDevice, stream));
   AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
   int rc = avsep_step_train_dev(st, st->waves, st->vecs, feat_dev, scale_dev, bias_dev, dfeat_dev, nullptr, nullptr, nullptr,
                                 nullptr, stream);
@@ -180,7 +181,7 @@ int avsep_step_eval_host(avsep_step* st, const float* waves_host, const float* v
                          void* stream_) {
   AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev && wav_host, "avsep_step_eval_host: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + 1) * st->B * st->L, cudaMemcpyHostToDevice, stream));
+  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + (st->mix_on_device ? 0 : 1)) * st->B * st->L, cudaMemcpyHostToDevice, stream));
   AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
   int rc = avsep_step_eval_dev(st, st->waves, st->vecs, feat_dev, scale_dev, bias_dev, binary_mask, mask_thres, st->wav, stream);
   if (rc) return rc;
@@ -190,6 +191,12 @@ int avsep_step_eval_host(avsep_step* st, const float* waves_host, const float* v
 }
 
 avsep_plan* avsep_step_plan(avsep_step* st) { return st ? st->plan : nullptr; }
+
+int avsep_step_set_mix_on_device(avsep_step* st, int enable) {
+  AVSEP_REQUIRE(st != nullptr, "avsep_step_set_mix_on_device: step is null");
+  st->mix_on_device = enable ? 1 : 0;
+  return AVSEP_OK;
+}
 
 const float* avsep_step_buffer(const avsep_step* st, int which) {
   if (!st) return nullptr;

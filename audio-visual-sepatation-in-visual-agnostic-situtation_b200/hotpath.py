@@ -196,6 +196,11 @@ class Step:
         self.T = 1 + wave_len // ops.HOP
         self.out_len = ops.HOP * (self.T - 1)
 
+    def set_mix_on_device(self, enable: bool = True):
+        """waves arguments become [N, B, L] (sources only); the mixture is summed on the GPU (dataset/music.py:127)."""
+        check(lib.avsep_step_set_mix_on_device(self._h, int(bool(enable))), "avsep_step_set_mix_on_device")
+        self.mix_on_device = bool(enable)
+
     def close(self):
         if getattr(self, "_h", None):
             torch.cuda.synchronize()

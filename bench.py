@@ -301,7 +301,7 @@ def main_ours(args, rank, world, local):
     # training loop), so the copy of step i+1 overlaps the kernels of step i; the loss of step i is read on
     # the host before its Step object is reused for step i+2.
     if eval_mode:
-        def run_e2e(k):
+        def run_e2e(k, mix_on_device=False):
             for _ in range(k):
                 step_host()
             return 0.0
@@ -313,34 +313,50 @@ def main_ours(args, rank, world, local):
                  dict(step=step_b, stream=torch.cuda.Stream(), dfeat=torch.empty_like(feat), loss=torch.zeros(1).pin_memory(),
                       dvecs=torch.empty((B, N, K)).pin_memory())]
         pipe_depth = 2
+        sources_host = waves_host[1:]                              # [N, B, L] view of the same pinned buffer
 
-        def run_e2e(k):
+        def run_e2e(k, mix_on_device):
+            for p in pipes:
+                p["step"].set_mix_on_device(mix_on_device)
+            src = sources_host if mix_on_device else waves_host
             for i in range(k):
                 p = pipes[i % 2]
                 p["stream"].synchronize()                          # step i-2 done: its loss is on the host now
                 _ = float(p["loss"][0])
                 with torch.cuda.stream(p["stream"]):
-                    p["step"].train_host_async(waves_host, vecs_host, feat, scale, bias, p["dfeat"], p["loss"], p["dvecs"])
+                    p["step"].train_host_async(src, vecs_host, feat, scale, bias, p["dfeat"], p["loss"], p["dvecs"])
             for p in pipes:
                 p["stream"].synchronize()
             return float(pipes[(k - 1) % 2]["loss"][0])
-    torch.cuda.synchronize()
-    run_e2e(4)
-    barrier()
-    t0 = time.perf_counter()
-    loss_host = run_e2e(args.steps)
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    barrier()
-    ms_e2e = parallel.max_over_ranks(wall_ms, device=dev)
+
+    def timed_e2e(mix_on_device):
+        torch.cuda.synchronize()
+        run_e2e(4, mix_on_device)
+        barrier()
+        t0 = time.perf_counter()
+        lh = run_e2e(args.steps, mix_on_device)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        return parallel.max_over_ranks(wall, device=dev), lh
+
+    # primary: the host supplies the N source waveforms, the mixture (their sum, dataset/music.py:127) is formed on
+    # the GPU inside the staging kernel; secondary: the host also supplies the mixture waveform (N+1 signals H2D)
+    ms_e2e, loss_host = timed_e2e(True)
+    ms_e2e_full, loss_host_full = timed_e2e(False) if not eval_mode else (ms_e2e, loss_host)
     if not eval_mode:
+        for p in pipes:
+            p["step"].set_mix_on_device(False)
         assert abs(loss_host - loss_val) <= 1e-6 * max(abs(loss_val), 1.0), (loss_host, loss_val)
+        assert abs(loss_host_full - loss_val) <= 1e-6 * max(abs(loss_val), 1.0), (loss_host_full, loss_val)
     for _ in range(40):                                            # keep the GPU loaded until a few more samples land
         step_dev()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
-    h2d = waves_host.numel() * 4 + vecs_host.numel() * 4
+    e2e_full_value = B * world * args.steps / (ms_e2e_full * 1e-3)
+    h2d_full = waves_host.numel() * 4 + vecs_host.numel() * 4
+    h2d = (h2d_full if eval_mode else waves_host[1:].numel() * 4 + vecs_host.numel() * 4)
     d2h = (wav_host.numel() * 4) if eval_mode else (4 + dvecs_host.numel() * 4)
     if world > 1:
         gl = parallel.global_mean_loss(torch.tensor(loss_val, device=dev), B)   # the path's only collective: 2 scalars
@@ -419,8 +435,10 @@ def main_ours(args, rank, world, local):
                         l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                      pipeline_depth=pipe_depth, timer="host wall clock around the K steps, synchronised on both sides",
-                     api="avsep_step_train_host_async (C-ABI, pinned host waveforms + K-vectors in, loss + dvecs out), "
-                         "2 steps in flight on 2 streams"),
+                     api="avsep_step_train_host_async (C-ABI): pinned host SOURCE waveforms [N,B,L] + K-vectors in, mixture summed "
+                         "on the GPU (avsep_step_set_mix_on_device), loss + dvecs out; 2 steps in flight on 2 streams",
+                     with_mixture_h2d=dict(value=e2e_full_value, ms_per_step=ms_e2e_full / args.steps, h2d_bytes_per_step=h2d_full,
+                                           note="same call with the mixture waveform also supplied by the host, [N+1,B,L]")),
             gpu_launches=int(launches), clocks=clocks, loss=loss_val, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline)
         print(json.dumps(line), flush=True)
     step.close()

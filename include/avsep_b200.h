@@ -108,7 +108,8 @@ int avsep_debug_gemm_only(avsep_plan* plan, int inverse, int S, float* out_dev, 
 int avsep_debug_basis(avsep_plan* plan, int inverse, float* out_host);
 /* staged forward operand (hi + lo) of signal s as fp32 on the host: out_host [T, 1024] */
 int avsep_debug_staged_frames(avsep_plan* plan, int s, float* out_host);
-/* selects the K-block of the GEMM pipeline: 32 (64B swizzle, 4 stages) or 64 (128B swizzle, 2 stages) */
+/* selects the K-block of the GEMM pipeline: 16 (32B swizzle, 9 stages), 32 (64B swizzle, 4 stages) or
+ * 64 (128B swizzle, 2 stages) */
 int avsep_plan_set_kblock(avsep_plan* plan, int kblock);
 
 /* ---- K2: log-frequency warp + derivations ------------------------------------------------- */
@@ -219,6 +220,10 @@ int avsep_step_eval_dev(avsep_step* step, const float* waves_dev, const float* v
  * 1 mix re, 2 mix im [B,512,T], 3 mag_mix_w, 4 log_mag_mix, 5 weights [B,256,T], 6 gt [N,B,256,T],
  * 7 pred masks [N,B,256,T] */
 const float* avsep_step_buffer(const avsep_step* step, int which);
+/* enable = 1: the `waves` argument of every step call holds only the N sources, [N, B, wave_len]; the mixture
+ * (dataset/music.py:127: the sum of the sources) is formed on the GPU inside the staging kernel, which saves
+ * 1/(N+1) of the H2D bytes.  Default 0: waves = [N+1, B, wave_len] with the mixture at index 0. */
+int avsep_step_set_mix_on_device(avsep_step* step, int enable);
 /* the STFT / iSTFT plan the step owns (borrowed) */
 avsep_plan* avsep_step_plan(avsep_step* step);
 

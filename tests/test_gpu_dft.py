@@ -63,7 +63,7 @@ def test_basis_tables():
     plan.close()
 
 
-@pytest.mark.parametrize("kblock,overlap", [(32, True), (64, True), (32, False)])
+@pytest.mark.parametrize("kblock,overlap", [(32, True), (64, True), (16, True), (32, False)])
 def test_raw_gemm_matches_staged_operands(kblock, overlap):
     """Isolates the tensor-core pipeline: raw accumulators vs (hi+lo basis) @ (hi+lo staged frames) in float64."""
     if not overlap:

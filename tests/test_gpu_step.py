@@ -81,6 +81,16 @@ def test_train_step_vs_oracle():
     dv_host = torch.empty((B, N, K)).pin_memory()
     lh = st.train_host(wh, vh, tfeat, c(scale), c(bias), dfeat2, dv_host)
     assert lh == float(loss) and torch.equal(dfeat, dfeat2) and torch.equal(dv_host.cuda(), dvecs)
+    # mixture formed on the GPU from the N sources (dataset/music.py:127): same bits for N = 2 (one IEEE add)
+    st.set_mix_on_device(True)
+    loss3 = torch.empty(1, device="cuda")
+    dfeat3 = torch.empty_like(dfeat)
+    st.train_dev(c(np.ascontiguousarray(waves[1:])), c(vecs), tfeat, c(scale), c(bias), dfeat3, None, None, None, loss3)
+    torch.cuda.synchronize()
+    assert float(loss3) == float(loss) and torch.equal(dfeat3, dfeat)
+    lh2 = st.train_host(torch.from_numpy(np.ascontiguousarray(waves[1:])).pin_memory(), vh, tfeat, c(scale), c(bias), dfeat2, dv_host)
+    assert lh2 == float(loss)
+    st.set_mix_on_device(False)
     st.close()
 
 

@@ -1,0 +1,23 @@
+"""GPU: time the DFT GEMM kernel alone (forward and inverse epilogues) for each K-block / stage-count variant."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import avsep_b200 as av
+import bench
+
+S, L = 240, 65535
+lib, chk = av._lib.lib, av._lib.check
+w = (torch.rand((S, L), device="cuda") - 0.5)
+plan = av.Plan(S, L)
+mag, ph = av.stft(w, plan=plan)
+wav = av.istft(mag, ph, plan=plan)          # stages the inverse operand
+torch.cuda.synchronize()
+stream = torch.cuda.current_stream().cuda_stream
+ref_mag, ref_wav = mag.clone(), wav.clone()
+for kb in (16, 32, 64):
+    plan.set_kblock(kb)
+    t_f = bench.time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan.handle, 0, S, mag.data_ptr(), stream)), 20, warmup=3)
+    t_i = bench.time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan.handle, 1, S, wav.data_ptr(), stream)), 20, warmup=3)
+    ok = torch.equal(mag, ref_mag), float((wav - ref_wav).abs().max())
+    tf = 3 * 2 * 1024 * 1024 * 256 * S / 1e12
+    print(f"kblock {kb:2d}: fwd {t_f*1e3:7.1f} us ({tf/t_f*1e3:7.1f} TFLOP/s executed)  inv {t_i*1e3:7.1f} us ({tf/t_i*1e3:7.1f})  same-bits-fwd={ok[0]} inv-maxdiff={ok[1]:.2e}")
