@@ -59,11 +59,13 @@ SIGNATURES = {
     "avsep_synth_scratch_bytes": (_SZ, [_I, _I, _I, _I]),
     "avsep_synth_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "avsep_synth_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "avsep_synth_train": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "avsep_synth_nosum": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "avsep_synth_pixelwise": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "avsep_loss_scratch_bytes": (_SZ, [_I, _SZ]),
     "avsep_loss_forward": (_I, [_I, _P, _P, _P, _I, _SZ, _P, _P, _P]),
     "avsep_loss_backward": (_I, [_I, _P, _P, _P, _I, _SZ, _P, _P, _P]),
+    "avsep_scale_if_needed": (_I, [_P, _SZ, _P, _P]),
     "avsep_pit_lossmat": (_I, [_I, _P, _P, _P, _I, _SZ, _I, _P, _P]),
     "avsep_step_create": (_I, [c_void_pp, _I, _I, _I, _I]),
     "avsep_step_destroy": (_I, [_P]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "avsep_step_buffer": (_P, [_P, _I]),
     "avsep_step_plan": (_P, [_P]),
     "avsep_step_set_mix_on_device": (_I, [_P, _I]),
+    "avsep_step_set_fused_train": (_I, [_P, _I]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -91,6 +91,20 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(int kind, PtrLis
   }
 }
 
+// x *= g[0] unless g[0] == 1 (then the kernel touches no memory): lets a fused forward+backward hand out gradients
+// computed for an upstream gradient of 1 and still honour an arbitrary upstream scalar without a host sync.
+__global__ void __launch_bounds__(256) scale_if_needed_kernel(float* __restrict__ x, size_t n4, size_t n, const float* __restrict__ g) {
+  const float s = g[0];
+  if (s == 1.0f) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) x[i] *= s;
+}
+
 // PIT: lossmat[b][i][j] = mean_p w[b,p,i] * l(pred[b,p,j], tgt[b,p,i]); sources innermost.
 template <int S>
 __global__ void __launch_bounds__(256) pit_lossmat_kernel(int kind, const float* __restrict__ preds, const float* __restrict__ tgts,
@@ -189,6 +203,18 @@ int avsep_loss_backward(int loss_kind, const float* const* preds_dev, const floa
   const unsigned grid = (unsigned)std::min<size_t>((numel + LOSS_THREADS - 1) / LOSS_THREADS, (size_t)148 * 16);
   loss_bwd_kernel<<<grid, LOSS_THREADS, 0, (cudaStream_t)stream>>>(loss_kind, L, weight_dev, N, numel, gscale_dev,
                                                                    (float)(1.0 / ((double)numel * (double)N)));
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+int avsep_scale_if_needed(float* x_dev, size_t n, const float* gscale_dev, void* stream) {
+  AVSEP_REQUIRE(x_dev && gscale_dev, "avsep_scale_if_needed: null argument");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (n == 0) return AVSEP_OK;
+  const size_t n4 = ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) ? n / 4 : 0;
+  const unsigned grid = (unsigned)std::min<size_t>((n4 + 255) / 256 + 1, (size_t)148 * 8);
+  scale_if_needed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, n4, n, gscale_dev);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }

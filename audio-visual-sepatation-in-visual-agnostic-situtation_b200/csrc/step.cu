@@ -19,6 +19,10 @@ int synth_forward_impl(const float* feat, const float* vecs, const float* scale,
                        cudaStream_t stream);
 int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
               int reim_count, void* stream, int mix_B, int mix_N);
+bool synth_train_supported(int K, int HW, const float* dfeat);
+int synth_train_impl(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int N, int K, int HW,
+                     int act, int loss_kind, const float* gt, const float* weight, const float* gscale, float* pred, float* loss,
+                     float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch, cudaStream_t stream);
 int synth_backward_impl(const float* feat, const float* vecs, const float* scale, int B, int N, int K, int HW, int act,
                         int loss_kind, const float* pred, const float* gt, const float* weight, const float* gscale,
                         const float* dz, float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch,
@@ -28,6 +32,7 @@ int synth_backward_impl(const float* feat, const float* vecs, const float* scale
 struct avsep_step {
   int B = 0, N = 0, K = 0, L = 0, T = 0, HW = 0, out_len = 0;
   int mix_on_device = 0;      // waves arguments hold only the N sources; the mixture is summed on the GPU
+  int no_fused_train = 0;     // debugging / A-B timing: run the separate forward and backward kernels
   avsep_plan* plan = nullptr;
   float* waves = nullptr;     // [N+1, B, L]  (index 0 = mixture)
   float* vecs = nullptr;      // [B, N, K]
@@ -52,7 +57,8 @@ struct avsep_step {
 using namespace avsep;
 
 static int step_forward_common(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
-                               const float* scale_dev, const float* bias_dev, bool need_reim, cudaStream_t stream) {
+                               const float* scale_dev, const float* bias_dev, bool need_reim, cudaStream_t stream,
+                               bool with_synth = true) {
   const int B = st->B, N = st->N;
   int rc = stft_impl(st->plan, waves_dev, (N + 1) * B, st->mag, nullptr, need_reim ? st->mix_re : nullptr,
                      need_reim ? st->mix_im : nullptr, B, stream, st->mix_on_device ? B : 0, st->mix_on_device ? N : 0);
@@ -68,7 +74,7 @@ static int step_forward_common(avsep_step* st, const float* waves_dev, const flo
     gts[n] = st->gt + (size_t)n * B * img;
   }
   rc = prepare_impl(st->mag, mags, N, B, st->T, 1, 1, 1, st->mix_w, mags_w, st->log_mix, st->weights, gts, stream);
-  if (rc) return rc;
+  if (rc || !with_synth) return rc;
   return synth_forward_impl(feat_dev, vecs_dev, scale_dev, bias_dev, B, N, st->K, st->HW, AVSEP_ACT_SIGMOID, st->pred,
                             AVSEP_LOSS_BCE, st->gt, st->weights, st->loss, st->scratch, stream);
 }
@@ -130,9 +136,15 @@ int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* ve
                          float* dbias_dev, float* loss_dev, void* stream_) {
   AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_train_dev: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, false, stream);
+  const bool fused = dfeat_dev != nullptr && synth_train_supported(st->K, st->HW, dfeat_dev) && !st->no_fused_train;
+  int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, false, stream, !fused);
   if (rc) return rc;
-  rc = synth_backward_impl(feat_dev, vecs_dev, scale_dev, st->B, st->N, st->K, st->HW, AVSEP_ACT_SIGMOID, AVSEP_LOSS_BCE,
+  if (fused)
+    rc = synth_train_impl(feat_dev, vecs_dev, scale_dev, bias_dev, st->B, st->N, st->K, st->HW, AVSEP_ACT_SIGMOID, AVSEP_LOSS_BCE,
+                          st->gt, st->weights, nullptr, st->pred, st->loss, dfeat_dev, dvecs_dev ? dvecs_dev : st->dvecs,
+                          dscale_dev ? dscale_dev : st->dscale, dbias_dev ? dbias_dev : st->dbias, st->scratch, stream);
+  else
+    rc = synth_backward_impl(feat_dev, vecs_dev, scale_dev, st->B, st->N, st->K, st->HW, AVSEP_ACT_SIGMOID, AVSEP_LOSS_BCE,
                            st->pred, st->gt, st->weights, st->one, nullptr, dfeat_dev, dvecs_dev ? dvecs_dev : st->dvecs,
                            dscale_dev ? dscale_dev : st->dscale, dbias_dev ? dbias_dev : st->dbias, st->scratch, stream);
   if (rc) return rc;
@@ -191,6 +203,12 @@ int avsep_step_eval_host(avsep_step* st, const float* waves_host, const float* v
 }
 
 avsep_plan* avsep_step_plan(avsep_step* st) { return st ? st->plan : nullptr; }
+
+int avsep_step_set_fused_train(avsep_step* st, int enable) {
+  AVSEP_REQUIRE(st != nullptr, "avsep_step_set_fused_train: step is null");
+  st->no_fused_train = enable ? 0 : 1;
+  return AVSEP_OK;
+}
 
 int avsep_step_set_mix_on_device(avsep_step* st, int enable) {
   AVSEP_REQUIRE(st != nullptr, "avsep_step_set_mix_on_device: step is null");

@@ -315,6 +315,179 @@ __global__ void __launch_bounds__(256) synth_bwd_final_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused training step: forward + loss + backward with ONE read of feat_sound from HBM
+// ---------------------------------------------------------------------------------------------
+// The backward needs dz = dL/dz, which depends on z = sum over ALL K channels, so feat is needed twice.  Each
+// thread parks its 32 x float4 feat values in a thread-private shared-memory column during pass 1 (z), then
+// pass 2 reads them back for S[n][k] = sum dz * feat and streams dfeat = sum_n dz[n] * vec[n][k] * scale[k]
+// out.  DRAM traffic: feat in + dfeat out + the small mask tensors -- the separate fwd + bwd kernels read feat
+// twice.  The gradient is computed for upstream gradient gscale (1 when the loss is the root of backward).
+constexpr int SYN_TR_THREADS = 128;
+constexpr int SYN_TR_GROUPS = 4;                       // pixel groups of 128 x 4 px walked by one CTA
+constexpr int SYN_TR_SMEM = 32 * SYN_TR_THREADS * 16;  // 64 KB staging
+
+template <int NS>
+__global__ void __launch_bounds__(SYN_TR_THREADS, 3)
+synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
+                   const float* __restrict__ bias, int B, int K, int HW, int act, int loss_kind, const float* __restrict__ gt,
+                   const float* __restrict__ weight, const float* __restrict__ gscale, float inv_count, float* __restrict__ pred,
+                   double* __restrict__ loss_partial, float* __restrict__ dfeat, float* __restrict__ s_partial,
+                   float* __restrict__ dz_partial, int Kp) {
+  extern __shared__ float4 stage[];                    // [32][SYN_TR_THREADS], column = thread (private)
+  __shared__ float vs[NS][SYN_KCHUNK];
+  __shared__ float red[SYN_TR_THREADS / 32][NS * SYN_KCHUNK + NS];
+  __shared__ double lred[32];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < NS * SYN_KCHUNK; i += blockDim.x) {
+    const int n = i / SYN_KCHUNK, k = i % SYN_KCHUNK;
+    vs[n][k] = (k < K) ? vecs[((size_t)b * NS + n) * K + k] * (scale ? scale[k] : 1.f) : 0.f;
+  }
+  __syncthreads();
+  const float bz = bias ? bias[0] : 0.f;
+  const float g = (gscale ? gscale[0] : 1.f) * inv_count;
+  const float* fbase = feat + (size_t)b * K * HW;
+  float* dbase = dfeat + (size_t)b * K * HW;
+  float S[NS][SYN_KCHUNK];
+  float dzs[NS];
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    dzs[n] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k) S[n][k] = 0.f;
+  }
+  float lsum = 0.f;
+#pragma unroll 1
+  for (int grp = 0; grp < SYN_TR_GROUPS; ++grp) {
+    const int px = ((blockIdx.x * SYN_TR_GROUPS + grp) * SYN_TR_THREADS + tid) * 4;
+    if (px >= HW) continue;
+    // ---- pass 1: z[n] = sum_k vs[n][k] * feat[k]; park feat in shared memory -----------------------------
+    float z[NS][4];
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) z[n][e] = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < SYN_KCHUNK; kc += SYN_BWD_LOADS) {
+      float4 f[SYN_BWD_LOADS];
+#pragma unroll
+      for (int j = 0; j < SYN_BWD_LOADS; ++j)
+        f[j] = (kc + j < K) ? ld_stream(reinterpret_cast<const float4*>(fbase + (size_t)(kc + j) * HW + px))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < SYN_BWD_LOADS; ++j) {
+        stage[(kc + j) * SYN_TR_THREADS + tid] = f[j];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const float c = vs[n][kc + j];
+          z[n][0] = fmaf(c, f[j].x, z[n][0]);
+          z[n][1] = fmaf(c, f[j].y, z[n][1]);
+          z[n][2] = fmaf(c, f[j].z, z[n][2]);
+          z[n][3] = fmaf(c, f[j].w, z[n][3]);
+        }
+      }
+    }
+    // ---- activation, loss, dz --------------------------------------------------------------------------------
+    float w[4] = {1.f, 1.f, 1.f, 1.f};
+    if (weight) {
+      const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
+      w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+    }
+    float dz[NS][4];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      const size_t o = ((size_t)n * B + b) * HW + px;
+      const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
+      const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+      float pr[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        pr[e] = act_apply(act, z[n][e] + bz);
+        lsum += w[e] * loss_elem(loss_kind, pr[e], tt[e]);
+        float d = g * w[e] * loss_grad(loss_kind, pr[e], tt[e]);
+        if (act == AVSEP_ACT_SIGMOID) d *= (1.f - pr[e]) * pr[e];
+        dz[n][e] = d;
+      }
+      *reinterpret_cast<float4*>(pred + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+      dzs[n] += (dz[n][0] + dz[n][1]) + (dz[n][2] + dz[n][3]);
+    }
+    // ---- pass 2: dfeat out, S accumulation from the parked feat ------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k) {
+      if (k < K) {
+        const float4 f = stage[k * SYN_TR_THREADS + tid];
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const float c = vs[n][k];
+          o4.x = fmaf(c, dz[n][0], o4.x);
+          o4.y = fmaf(c, dz[n][1], o4.y);
+          o4.z = fmaf(c, dz[n][2], o4.z);
+          o4.w = fmaf(c, dz[n][3], o4.w);
+          S[n][k] += (dz[n][0] * f.x + dz[n][1] * f.y) + (dz[n][2] * f.z + dz[n][3] * f.w);
+        }
+        st_stream(reinterpret_cast<float4*>(dbase + (size_t)k * HW + px), o4);
+      }
+    }
+  }
+  // ---- CTA reductions --------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k) {
+      const float r = warp_sum(S[n][k]);
+      if (lane == 0) red[warp][n * SYN_KCHUNK + k] = r;
+    }
+    const float r = warp_sum(dzs[n]);
+    if (lane == 0) red[warp][NS * SYN_KCHUNK + n] = r;
+  }
+  const double ltot = block_sum<double>((double)lsum, lred);      // contains the __syncthreads that publishes red[][]
+  const size_t cta = (size_t)b * gridDim.x + blockIdx.x;
+  if (tid == 0) loss_partial[cta] = ltot;
+  for (int i = tid; i < NS * SYN_KCHUNK + NS; i += blockDim.x) {
+    float r = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < SYN_TR_THREADS / 32; ++wq) r += red[wq][i];
+    if (i < NS * SYN_KCHUNK) {
+      const int n = i / SYN_KCHUNK, k = i % SYN_KCHUNK;
+      if (k < K) s_partial[(cta * NS + n) * Kp + k] = r;
+    } else {
+      dz_partial[cta * NS + (i - NS * SYN_KCHUNK)] = r;
+    }
+  }
+}
+
+// One finalize launch for everything small: block k < K: dvecs[:, :, k] and dscale[k]; block K: dbias; block K+1: loss.
+__global__ void __launch_bounds__(256)
+synth_finalize_kernel(const float* __restrict__ s_partial, const float* __restrict__ dz_partial, const double* __restrict__ loss_partial,
+                      const float* __restrict__ vecs, const float* __restrict__ scale, int B, int N, int K, int Kp, int chunks,
+                      int n_loss, double inv_count, float* __restrict__ dvecs, float* __restrict__ dscale, float* __restrict__ dbias,
+                      float* __restrict__ loss) {
+  __shared__ double red[32];
+  const int blk = blockIdx.x;
+  double acc = 0.0;
+  if (blk < K) {
+    for (int i = threadIdx.x; i < B * N; i += blockDim.x) {       // i = b * N + n
+      const int bb = i / N, n = i % N;
+      float t = 0.f;
+      for (int c = 0; c < chunks; ++c) t += s_partial[(((size_t)bb * chunks + c) * N + n) * Kp + blk];
+      if (dvecs) dvecs[(size_t)i * K + blk] = t * (scale ? scale[blk] : 1.f);
+      acc += (double)(t * vecs[(size_t)i * K + blk]);
+    }
+    const double tot = block_sum<double>(acc, red);
+    if (threadIdx.x == 0 && dscale) dscale[blk] = (float)tot;
+  } else if (blk == K) {
+    for (int i = threadIdx.x; i < B * chunks * N; i += blockDim.x) acc += (double)dz_partial[i];
+    const double tot = block_sum<double>(acc, red);
+    if (threadIdx.x == 0 && dbias) dbias[0] = (float)tot;
+  } else {
+    for (int i = threadIdx.x; i < n_loss; i += blockDim.x) acc += loss_partial[i];
+    const double tot = block_sum<double>(acc, red);
+    if (threadIdx.x == 0 && loss) loss[0] = (float)(tot * inv_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward_nosum / forward_pixelwise (inference helpers, synthesizer_net.py:21-38)
 // ---------------------------------------------------------------------------------------------
 __global__ void synth_nosum_kernel(const float* __restrict__ feat, const float* __restrict__ vec, const float* __restrict__ scale,
@@ -420,6 +593,44 @@ static int synth_backward_n(const float* feat, const float* vecs, const float* s
   return AVSEP_OK;
 }
 
+template <int NS>
+static int synth_train_n(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int K, int HW,
+                         int act, int loss_kind, const float* gt, const float* weight, const float* gscale, float* pred,
+                         float* loss, float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch, cudaStream_t stream) {
+  const SynthScratch lay = synth_scratch_layout(B, NS, K, HW);
+  char* sc = static_cast<char*>(scratch);
+  double* loss_partial = reinterpret_cast<double*>(sc + lay.loss_partial);
+  float* s_partial = reinterpret_cast<float*>(sc + lay.s_partial);
+  float* dz_partial = reinterpret_cast<float*>(sc + lay.dz_partial);
+  const int chunks = ceil_div(HW, SYN_TR_THREADS * 4 * SYN_TR_GROUPS);      // == lay.bwd_chunks (same 2048 px per CTA)
+  static_assert(SYN_TR_THREADS * SYN_TR_GROUPS == SYN_BWD_THREADS * SYN_BWD_ITERS, "scratch layout shared with the backward kernel");
+  auto kern = synth_train_kernel<NS>;
+  AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_TR_SMEM));
+  dim3 grid(chunks, B);
+  const float inv_count = (float)(1.0 / ((double)B * (double)HW * (double)NS));
+  kern<<<grid, SYN_TR_THREADS, SYN_TR_SMEM, stream>>>(feat, vecs, scale, bias, B, K, HW, act, loss_kind, gt, weight, gscale, inv_count,
+                                                       pred, loss_partial, dfeat, s_partial, dz_partial, lay.Kp);
+  AVSEP_LAUNCH_CHECK();
+  synth_finalize_kernel<<<K + 2, 256, 0, stream>>>(s_partial, dz_partial, loss_partial, vecs, scale, B, NS, K, lay.Kp, chunks,
+                                                    chunks * B, 1.0 / ((double)B * (double)HW * (double)NS), dvecs, dscale, dbias, loss);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+// fused forward + loss + backward (K <= 32, HW % 4 == 0, dfeat required); callers fall back to fwd + bwd otherwise
+bool synth_train_supported(int K, int HW, const float* dfeat) { return K <= SYN_KCHUNK && (HW % 4) == 0 && dfeat != nullptr; }
+
+int synth_train_impl(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int N, int K, int HW,
+                     int act, int loss_kind, const float* gt, const float* weight, const float* gscale, float* pred, float* loss,
+                     float* dfeat, float* dvecs, float* dscale, float* dbias, void* scratch, cudaStream_t stream) {
+  switch (N) {
+    case 1: return synth_train_n<1>(feat, vecs, scale, bias, B, K, HW, act, loss_kind, gt, weight, gscale, pred, loss, dfeat, dvecs, dscale, dbias, scratch, stream);
+    case 2: return synth_train_n<2>(feat, vecs, scale, bias, B, K, HW, act, loss_kind, gt, weight, gscale, pred, loss, dfeat, dvecs, dscale, dbias, scratch, stream);
+    case 3: return synth_train_n<3>(feat, vecs, scale, bias, B, K, HW, act, loss_kind, gt, weight, gscale, pred, loss, dfeat, dvecs, dscale, dbias, scratch, stream);
+    default: return synth_train_n<4>(feat, vecs, scale, bias, B, K, HW, act, loss_kind, gt, weight, gscale, pred, loss, dfeat, dvecs, dscale, dbias, scratch, stream);
+  }
+}
+
 int synth_forward_impl(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int N, int K, int HW,
                        int act, float* out, int loss_kind, const float* gt, const float* weight, float* loss, void* scratch,
                        cudaStream_t stream) {
@@ -489,6 +700,31 @@ int avsep_synth_backward(const float* feat_dev, const float* vecs_dev, const flo
   if (B == 0) return AVSEP_OK;
   return synth_backward_impl(feat_dev, vecs_dev, scale_dev, B, N, K, HW, activation, loss_kind, pred_dev, gt_dev, weight_dev,
                              gscale_dev, dz_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, scratch_dev, (cudaStream_t)stream);
+}
+
+int avsep_synth_train(const float* feat_dev, const float* vecs_dev, const float* scale_dev, const float* bias_dev, int B, int N,
+                      int K, int HW, int activation, int loss_kind, const float* gt_dev, const float* weight_dev,
+                      const float* gscale_dev, float* pred_dev, float* loss_dev, float* dfeat_dev, float* dvecs_dev,
+                      float* dscale_dev, float* dbias_dev, void* scratch_dev, void* stream) {
+  AVSEP_REQUIRE(feat_dev && vecs_dev && gt_dev && pred_dev && loss_dev && dfeat_dev && scratch_dev, "avsep_synth_train: null argument");
+  AVSEP_REQUIRE(N >= 1 && N <= AVSEP_MAX_SRC, "avsep_synth_train: N = %d outside [1, %d]", N, AVSEP_MAX_SRC);
+  AVSEP_REQUIRE(K >= 1 && K <= SYN_MAX_K, "avsep_synth_train: K = %d outside [1, %d]", K, SYN_MAX_K);
+  AVSEP_REQUIRE(B >= 0 && B <= 65535 && HW >= 4 && HW % 4 == 0, "avsep_synth_train: bad B = %d / HW = %d (HW must be a multiple of 4)", B, HW);
+  AVSEP_REQUIRE(loss_kind >= AVSEP_LOSS_L1 && loss_kind <= AVSEP_LOSS_BCE, "avsep_synth_train: unknown loss kind %d", loss_kind);
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (synth_train_supported(K, HW, dfeat_dev))
+    return synth_train_impl(feat_dev, vecs_dev, scale_dev, bias_dev, B, N, K, HW, activation, loss_kind, gt_dev, weight_dev, gscale_dev,
+                            pred_dev, loss_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, scratch_dev, st);
+  // K > 32: two passes over feat (forward, then backward from the saved activations)
+  rc = synth_forward_impl(feat_dev, vecs_dev, scale_dev, bias_dev, B, N, K, HW, activation, pred_dev, loss_kind, gt_dev, weight_dev,
+                          loss_dev, scratch_dev, st);
+  if (rc) return rc;
+  AVSEP_REQUIRE(gscale_dev != nullptr, "avsep_synth_train: gscale_dev is required when K > 32");
+  return synth_backward_impl(feat_dev, vecs_dev, scale_dev, B, N, K, HW, activation, loss_kind, pred_dev, gt_dev, weight_dev, gscale_dev,
+                             nullptr, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, scratch_dev, st);
 }
 
 int avsep_synth_nosum(const float* feat_dev, const float* vec_dev, const float* scale_dev, const float* bias_dev, int B, int K,

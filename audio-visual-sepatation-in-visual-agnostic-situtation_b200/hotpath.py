@@ -196,6 +196,10 @@ class Step:
         self.T = 1 + wave_len // ops.HOP
         self.out_len = ops.HOP * (self.T - 1)
 
+    def set_fused_train(self, enable: bool = True):
+        """False: run the separate synthesizer forward / backward kernels instead of the fused training kernel."""
+        check(lib.avsep_step_set_fused_train(self._h, int(bool(enable))), "avsep_step_set_fused_train")
+
     def set_mix_on_device(self, enable: bool = True):
         """waves arguments become [N, B, L] (sources only); the mixture is summed on the GPU (dataset/music.py:127)."""
         check(lib.avsep_step_set_mix_on_device(self._h, int(bool(enable))), "avsep_step_set_mix_on_device")

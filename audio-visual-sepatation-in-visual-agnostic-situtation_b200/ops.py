@@ -308,7 +308,12 @@ class _SynthMasks(torch.autograd.Function):
 
 
 class _SynthMasksLoss(torch.autograd.Function):
-    """Fused synthesizer + activation + list-form weighted loss; backward recomputes dz from the saved masks."""
+    """Fused synthesizer + activation + list-form weighted loss.
+
+    When feat_sound needs a gradient (and K <= 32) the forward call runs the fused training kernel: loss AND the
+    gradients for an upstream gradient of 1 come out of a single pass over feat_sound; backward only rescales them
+    by the actual upstream scalar (a no-op kernel when it is 1).  Otherwise forward saves the masks and backward
+    recomputes dz from them (second pass over feat_sound)."""
 
     @staticmethod
     def forward(ctx, feat, vecs, scale, bias, gt, weight, activation, loss_kind):
@@ -318,24 +323,50 @@ class _SynthMasksLoss(torch.autograd.Function):
         b = _cuda_f32(bias, "synth_loss: bias") if bias is not None else None
         g = _cuda_f32(gt, "synth_loss: gt_masks")
         w = _cuda_f32(weight, "synth_loss: weight") if weight is not None else None
-        out, loss = _synth_forward_raw(f, v, s, b, activation, loss_kind, g, w)
+        B, K = f.shape[0], f.shape[1]
+        HW = f[0, 0].numel()
+        N = v.shape[1]
         empty = torch.empty(0, device=f.device)
-        ctx.save_for_backward(f, v, s if s is not None else empty, out, g, w if w is not None else empty)
         ctx.has_scale, ctx.has_bias, ctx.has_weight = s is not None, b is not None, w is not None
         ctx.activation, ctx.loss_kind = activation, loss_kind
+        ctx.fused = bool(ctx.needs_input_grad[0]) and K <= 32 and HW % 4 == 0
+        if ctx.fused:
+            out = torch.empty((N, B) + tuple(f.shape[2:]), device=f.device, dtype=torch.float32)
+            loss = torch.zeros((), device=f.device, dtype=torch.float32)
+            dfeat = torch.empty_like(f)
+            dvecs = torch.empty_like(v)
+            dscale = torch.empty_like(s) if s is not None else None
+            dbias = torch.empty(1, device=f.device, dtype=torch.float32)
+            scratch = _scratch(B, N, K, HW, f.device)
+            check(lib.avsep_synth_train(f.data_ptr(), v.data_ptr(), _p(s), _p(b), B, N, K, HW, activation, loss_kind,
+                                        g.data_ptr(), _p(w), None, out.data_ptr(), loss.data_ptr(), dfeat.data_ptr(),
+                                        dvecs.data_ptr(), _p(dscale), dbias.data_ptr(), scratch.data_ptr(), _stream()),
+                  "avsep_synth_train")
+            ctx.save_for_backward(dfeat, dvecs, dscale if dscale is not None else empty, dbias)
+        else:
+            out, loss = _synth_forward_raw(f, v, s, b, activation, loss_kind, g, w)
+            ctx.save_for_backward(f, v, s if s is not None else empty, out, g, w if w is not None else empty)
         ctx.mark_non_differentiable(out)
         return loss, out
 
     @staticmethod
     def backward(ctx, gloss, _gout):
+        gs = _cuda_f32(gloss.reshape(1), "synth_loss backward: grad")
+        need = ctx.needs_input_grad
+        if ctx.fused:
+            dfeat, dvecs, dscale, dbias = ctx.saved_tensors
+            outs = [dfeat, dvecs if need[1] else None, dscale if (ctx.has_scale and need[2]) else None,
+                    dbias if (ctx.has_bias and need[3]) else None]
+            for t in outs:
+                if t is not None:
+                    check(lib.avsep_scale_if_needed(t.data_ptr(), t.numel(), gs.data_ptr(), _stream()), "avsep_scale_if_needed")
+            return outs[0], outs[1], outs[2], outs[3], None, None, None, None
         f, v, s, out, g, w = ctx.saved_tensors
         s = s if ctx.has_scale else None
         w = w if ctx.has_weight else None
         B, K = f.shape[0], f.shape[1]
         HW = f[0, 0].numel()
         N = v.shape[1]
-        gs = _cuda_f32(gloss.reshape(1), "synth_loss backward: grad")
-        need = ctx.needs_input_grad
         dfeat = torch.empty_like(f) if need[0] else None
         dvecs = torch.empty_like(v) if need[1] else None
         dscale = torch.empty_like(s) if (s is not None and need[2]) else None

@@ -158,6 +158,15 @@ int avsep_synth_backward(const float* feat_dev, const float* vecs_dev, const flo
                          float* dfeat_dev, float* dvecs_dev, float* dscale_dev, float* dbias_dev,
                          void* scratch_dev, void* stream);
 
+/* Fused training step of the synthesizer: forward + activation + list-form loss + full backward with ONE read of
+ * feat_dev from HBM (K <= 32; larger K runs the two kernels above).  Gradients are those of
+ * gscale_dev[0] * loss (NULL = 1, i.e. loss.backward()).  pred_dev [N,B,HW] receives the activations. */
+int avsep_synth_train(const float* feat_dev, const float* vecs_dev, const float* scale_dev, const float* bias_dev,
+                      int B, int N, int K, int HW, int activation, int loss_kind,
+                      const float* gt_dev, const float* weight_dev, const float* gscale_dev,
+                      float* pred_dev, float* loss_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
+                      float* dbias_dev, void* scratch_dev, void* stream);
+
 /* InnerProd.forward_nosum (synthesizer_net.py:21-26): out [B,K,HW] = vec*scale (x) feat + bias */
 int avsep_synth_nosum(const float* feat_dev, const float* vec_dev, const float* scale_dev,
                       const float* bias_dev, int B, int K, int HW, float* out_dev, void* stream);
@@ -175,6 +184,9 @@ int avsep_loss_forward(int loss_kind, const float* const* preds_dev, const float
 int avsep_loss_backward(int loss_kind, const float* const* preds_dev, const float* const* targets_dev,
                         const float* weight_dev, int N, size_t numel, const float* gscale_dev,
                         float* const* dpreds_dev, void* stream);
+
+/* x_dev[0..n) *= gscale_dev[0], skipped on the device when the scalar is exactly 1 (no host sync, no traffic) */
+int avsep_scale_if_needed(float* x_dev, size_t n, const float* gscale_dev, void* stream);
 
 /* PitWrapper(F.binary_cross_entropy) (models/criterion.py:74-231): per-sample S x S loss matrix.
  *   preds_dev, targets_dev, weights_dev [B, P, S] (sources innermost, as the reference stacks them)
@@ -224,6 +236,9 @@ const float* avsep_step_buffer(const avsep_step* step, int which);
  * (dataset/music.py:127: the sum of the sources) is formed on the GPU inside the staging kernel, which saves
  * 1/(N+1) of the H2D bytes.  Default 0: waves = [N+1, B, wave_len] with the mixture at index 0. */
 int avsep_step_set_mix_on_device(avsep_step* step, int enable);
+/* enable = 0: run the separate synthesizer forward and backward kernels instead of the fused training kernel
+ * (A/B timing and tests); default 1. */
+int avsep_step_set_fused_train(avsep_step* step, int enable);
 /* the STFT / iSTFT plan the step owns (borrowed) */
 avsep_plan* avsep_step_plan(avsep_step* step);
 

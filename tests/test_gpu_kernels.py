@@ -155,6 +155,28 @@ def test_fused_synth_loss_matches_reference_golden(golden, kind):
         assert relerr(masks[0].cpu().numpy(), g["pred0"]) < TOL and relerr(masks[1].cpu().numpy(), g["pred1"]) < TOL
 
 
+def test_fused_loss_with_upstream_scale_and_partial_grads(golden):
+    """(3 * err).backward(): the fused kernel's unit gradients are rescaled on the device; without a gradient on
+    feat_sound the two-pass path is taken and still matches."""
+    g = golden("synth")
+    feat, vecs, scale, bias, gts, wgt, _ = _synth_inputs()
+    m = _module(scale, bias)
+    tf = _cuda(feat).requires_grad_(True)
+    tv = _cuda(vecs).requires_grad_(True)
+    err, _ = m.forward_loss(tv, tf, [_cuda(t) for t in gts], _cuda(wgt), loss="bce")
+    (3.0 * err).backward()
+    assert relerr(tf.grad.cpu().numpy(), 3.0 * g["bce_dfeat"]) < TOL
+    assert relerr(tv.grad.cpu().numpy(), 3.0 * g["bce_dvecs"]) < TOL
+    assert relerr(m.scale.grad.cpu().numpy(), 3.0 * g["bce_dscale"]) < TOL
+    m2 = _module(scale, bias)
+    tv2 = _cuda(vecs).requires_grad_(True)
+    err2, _ = m2.forward_loss(tv2, _cuda(feat), [_cuda(t) for t in gts], _cuda(wgt), loss="bce")
+    err2.backward()
+    assert abs(float(err2.detach()) - float(g["bce_loss"])) / float(g["bce_loss"]) < TOL
+    assert relerr(tv2.grad.cpu().numpy(), g["bce_dvecs"]) < TOL
+    assert relerr(m2.scale.grad.cpu().numpy(), g["bce_dscale"]) < TOL
+
+
 @pytest.mark.parametrize("kind", ["bce", "l1"])
 def test_unfused_dropin_path_matches_reference_golden(golden, kind):
     """The reference's own call pattern (SoP++/main.py:203-209): per-source InnerProd, torch sigmoid, criterion."""

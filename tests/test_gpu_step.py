@@ -81,6 +81,16 @@ def test_train_step_vs_oracle():
     dv_host = torch.empty((B, N, K)).pin_memory()
     lh = st.train_host(wh, vh, tfeat, c(scale), c(bias), dfeat2, dv_host)
     assert lh == float(loss) and torch.equal(dfeat, dfeat2) and torch.equal(dv_host.cuda(), dvecs)
+    # separate forward / backward kernels (two passes over feat_sound) agree with the fused training kernel
+    st.set_fused_train(False)
+    loss4 = torch.empty(1, device="cuda")
+    dfeat4, dvecs4, dscale4, dbias4 = torch.empty_like(dfeat), torch.empty_like(dvecs), torch.empty_like(dscale), torch.empty_like(dbias)
+    st.train_dev(c(waves), c(vecs), tfeat, c(scale), c(bias), dfeat4, dvecs4, dscale4, dbias4, loss4)
+    torch.cuda.synchronize()
+    assert abs(float(loss4) - float(loss)) < 1e-6 * abs(float(loss))
+    assert relerr(dfeat4.cpu().numpy(), dfeat.cpu().numpy()) < 1e-5 and relerr(dvecs4.cpu().numpy(), dvecs.cpu().numpy()) < 1e-5
+    assert relerr(dscale4.cpu().numpy(), dscale.cpu().numpy()) < 1e-5 and abs(float(dbias4) - float(dbias)) < 1e-5 * abs(float(dbias))
+    st.set_fused_train(True)
     # mixture formed on the GPU from the N sources (dataset/music.py:127): same bits for N = 2 (one IEEE add)
     st.set_mix_on_device(True)
     loss3 = torch.empty(1, device="cuda")
