@@ -99,6 +99,22 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- cp.async (LDGSTS): global -> shared without staging registers ----------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// log(x) with MUFU.LG2: max 3 ulp outside [0.5, 2], abs error 2^-21.4 inside (CUDA math API) -- far inside the
+// 1e-4 max-norm budget of the path, and ~10x cheaper than logf
+__device__ __forceinline__ float fast_log(float x) { return __logf(x); }
+// log1p(x) for x >= 0: 4-term series below 2^-5 (rel. error < 3e-7), log(1 + x) above (rel. error < 2e-6)
+__device__ __forceinline__ float fast_log1p_pos(float x) {
+  if (x < 0.03125f) return x * (1.f - x * (0.5f - x * (0.33333334f - x * 0.25f)));
+  return __logf(1.f + x);
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");

@@ -327,7 +327,7 @@ constexpr int SYN_TR_GROUPS = 4;                       // pixel groups of 128 x 
 constexpr int SYN_TR_SMEM = 32 * SYN_TR_THREADS * 16;  // 64 KB staging
 
 template <int NS>
-__global__ void __launch_bounds__(SYN_TR_THREADS, 3)
+__global__ void __launch_bounds__(SYN_TR_THREADS, (NS <= 2 ? 3 : 2))
 synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
                    const float* __restrict__ bias, int B, int K, int HW, int act, int loss_kind, const float* __restrict__ gt,
                    const float* __restrict__ weight, const float* __restrict__ gscale, float inv_count, float* __restrict__ pred,
@@ -361,44 +361,48 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
   for (int grp = 0; grp < SYN_TR_GROUPS; ++grp) {
     const int px = ((blockIdx.x * SYN_TR_GROUPS + grp) * SYN_TR_THREADS + tid) * 4;
     if (px >= HW) continue;
-    // ---- pass 1: z[n] = sum_k vs[n][k] * feat[k]; park feat in shared memory -----------------------------
+    // ---- pass 0: all K 16-byte feat loads of this thread go straight to its shared-memory column with cp.async
+    //      (no staging registers, 32 loads in flight per thread) ----------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < SYN_KCHUNK; ++k)
+      if (k < K) cp_async_16(&stage[k * SYN_TR_THREADS + tid], fbase + (size_t)k * HW + px);
+    cp_async_commit();
+    // small streams overlap the feat loads
+    float w[4] = {1.f, 1.f, 1.f, 1.f};
+    if (weight) {
+      const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
+      w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+    }
+    float4 tgt[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) tgt[n] = *reinterpret_cast<const float4*>(gt + ((size_t)n * B + b) * HW + px);
+    cp_async_wait_all();
+    // ---- pass 1: z[n] = sum_k vs[n][k] * feat[k] ---------------------------------------------------------------------
     float z[NS][4];
 #pragma unroll
     for (int n = 0; n < NS; ++n)
 #pragma unroll
       for (int e = 0; e < 4; ++e) z[n][e] = 0.f;
 #pragma unroll
-    for (int kc = 0; kc < SYN_KCHUNK; kc += SYN_BWD_LOADS) {
-      float4 f[SYN_BWD_LOADS];
-#pragma unroll
-      for (int j = 0; j < SYN_BWD_LOADS; ++j)
-        f[j] = (kc + j < K) ? ld_stream(reinterpret_cast<const float4*>(fbase + (size_t)(kc + j) * HW + px))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < SYN_BWD_LOADS; ++j) {
-        stage[(kc + j) * SYN_TR_THREADS + tid] = f[j];
+    for (int k = 0; k < SYN_KCHUNK; ++k) {
+      if (k < K) {
+        const float4 f = stage[k * SYN_TR_THREADS + tid];
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
-          const float c = vs[n][kc + j];
-          z[n][0] = fmaf(c, f[j].x, z[n][0]);
-          z[n][1] = fmaf(c, f[j].y, z[n][1]);
-          z[n][2] = fmaf(c, f[j].z, z[n][2]);
-          z[n][3] = fmaf(c, f[j].w, z[n][3]);
+          const float c = vs[n][k];
+          z[n][0] = fmaf(c, f.x, z[n][0]);
+          z[n][1] = fmaf(c, f.y, z[n][1]);
+          z[n][2] = fmaf(c, f.z, z[n][2]);
+          z[n][3] = fmaf(c, f.w, z[n][3]);
         }
       }
     }
     // ---- activation, loss, dz --------------------------------------------------------------------------------
-    float w[4] = {1.f, 1.f, 1.f, 1.f};
-    if (weight) {
-      const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
-      w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
-    }
     float dz[NS][4];
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       const size_t o = ((size_t)n * B + b) * HW + px;
-      const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
-      const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+      const float tt[4] = {tgt[n].x, tgt[n].y, tgt[n].z, tgt[n].w};
       float pr[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {

@@ -192,11 +192,11 @@ __global__ void __launch_bounds__(PREP_TX * PREP_TY) prepare_vec_kernel(const Pr
       const size_t o = out_off + (size_t)h * p.T + w0;
       const float* mx = v[0].v;
       if (p.mix_w) *reinterpret_cast<float4*>(p.mix_w + o) = make_float4(mx[0], mx[1], mx[2], mx[3]);
-      if (p.log_mix) *reinterpret_cast<float4*>(p.log_mix + o) = make_float4(logf(mx[0]), logf(mx[1]), logf(mx[2]), logf(mx[3]));
+      if (p.log_mix) *reinterpret_cast<float4*>(p.log_mix + o) = make_float4(fast_log(mx[0]), fast_log(mx[1]), fast_log(mx[2]), fast_log(mx[3]));
       if (p.weights) {
         float wv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) wv[e] = p.weighted ? fminf(fmaxf(log1pf(mx[e]), 1e-3f), 10.f) : 1.f;
+        for (int e = 0; e < 4; ++e) wv[e] = p.weighted ? fminf(fmaxf(fast_log1p_pos(mx[e]), 1e-3f), 10.f) : 1.f;
         *reinterpret_cast<float4*>(p.weights + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
       }
 #pragma unroll
