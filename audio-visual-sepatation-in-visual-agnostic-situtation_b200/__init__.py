@@ -12,19 +12,20 @@ The directory name carries the upstream repo name (hyphens), so import it throug
 from . import _lib
 from ._lib import AvsepError, LIB_PATH
 from . import ops
-from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pit_lossmat, separate, stft,
+from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pit_loss, pit_lossmat, separate, stft,
                   synth_masks, synth_masks_loss, synth_nosum, synth_pixelwise)
 from . import modules
 from .modules import BCELoss, BaseLoss, Bias, InnerProd, L1Loss, L2Loss, PitWrapper, activate
 from . import hotpath
-from .hotpath import (Step, _mix_n_and_stft, _stft, calc_metrics, istft_reconstruction, prepare, stft_batch, warp, warpgrid)
+from .hotpath import (Step, _mix_n_and_stft, _stft, assemble_windows, calc_metrics, clip_windows, istft_reconstruction, prepare,
+                      separate_long_clip, stft_batch, warp, warpgrid)
 from . import parallel
 
 __all__ = [
     "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel",
     "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
     "stft", "istft", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
-    "_stft", "_mix_n_and_stft", "stft_batch", "Step",
-    "synth_masks", "synth_masks_loss", "synth_nosum", "synth_pixelwise", "list_loss", "pit_lossmat",
+    "_stft", "_mix_n_and_stft", "stft_batch", "Step", "clip_windows", "assemble_windows", "separate_long_clip",
+    "synth_masks", "synth_masks_loss", "synth_nosum", "synth_pixelwise", "list_loss", "pit_loss", "pit_lossmat",
     "InnerProd", "Bias", "BaseLoss", "BCELoss", "L1Loss", "L2Loss", "PitWrapper", "activate",
 ]

@@ -67,6 +67,7 @@ SIGNATURES = {
     "avsep_loss_backward": (_I, [_I, _P, _P, _P, _I, _SZ, _P, _P, _P]),
     "avsep_scale_if_needed": (_I, [_P, _SZ, _P, _P]),
     "avsep_pit_lossmat": (_I, [_I, _P, _P, _P, _I, _SZ, _I, _P, _P]),
+    "avsep_pit_backward": (_I, [_I, _P, _P, _P, _P, _P, _I, _SZ, _I, _P, _P]),
     "avsep_step_create": (_I, [c_void_pp, _I, _I, _I, _I]),
     "avsep_step_destroy": (_I, [_P]),
     "avsep_step_train_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -139,6 +139,37 @@ __global__ void __launch_bounds__(256) pit_lossmat_kernel(int kind, const float*
     }
 }
 
+// d loss[b] / d pred[b,p,j] for loss[b] = (1/S) sum_i lossmat[b][i][perm_b(i)]: prediction j is matched with
+// target i = inv_perm[b][j]  ->  g[b] / (S P) * w[b,p,i] * l'(pred[b,p,j], tgt[b,p,i])
+template <int S>
+__global__ void __launch_bounds__(256) pit_bwd_kernel(int kind, const float* __restrict__ preds, const float* __restrict__ tgts,
+                                                       const float* __restrict__ wts, const int* __restrict__ inv_perm,
+                                                       const float* __restrict__ gloss, size_t P, float* __restrict__ dpreds) {
+  const int b = blockIdx.y;
+  int ip[S];
+#pragma unroll
+  for (int j = 0; j < S; ++j) ip[j] = inv_perm[b * S + j];
+  const float g = gloss[b] / ((float)S * (float)P);
+  const size_t off = (size_t)b * P * S;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    float pr[S], tg[S], ww[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      pr[s] = preds[off + p * S + s];
+      tg[s] = tgts[off + p * S + s];
+      ww[s] = wts[off + p * S + s];
+    }
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      float t = tg[0], w = ww[0];
+#pragma unroll
+      for (int i = 1; i < S; ++i)
+        if (ip[j] == i) { t = tg[i]; w = ww[i]; }
+      dpreds[off + p * S + j] = g * w * l_grad(kind, pr[j], t);
+    }
+  }
+}
+
 __global__ void pit_fin_kernel(const double* __restrict__ partial, int chunks, int SS, double inv_P, float* __restrict__ lossmat) {
   const int b = blockIdx.x;
   const int e = threadIdx.x;
@@ -245,6 +276,27 @@ int avsep_pit_lossmat(int loss_kind, const float* preds_dev, const float* target
   pit_fin_kernel<<<B, 32, 0, stream>>>(partial, chunks, S * S, 1.0 / (double)P, lossmat_dev);
   AVSEP_LAUNCH_CHECK();
   AVSEP_CUDA(cudaFreeAsync(partial, stream));
+  return AVSEP_OK;
+}
+
+int avsep_pit_backward(int loss_kind, const float* preds_dev, const float* targets_dev, const float* weights_dev,
+                       const int* inv_perm_dev, const float* gloss_dev, int B, size_t P, int S, float* dpreds_dev, void* stream_) {
+  AVSEP_REQUIRE(loss_kind >= AVSEP_LOSS_L1 && loss_kind <= AVSEP_LOSS_BCE, "avsep_pit_backward: unknown loss kind %d", loss_kind);
+  AVSEP_REQUIRE(preds_dev && targets_dev && weights_dev && inv_perm_dev && gloss_dev && dpreds_dev, "avsep_pit_backward: null tensor");
+  AVSEP_REQUIRE(S >= 1 && S <= 4, "avsep_pit_backward: S = %d outside [1, 4]", S);
+  AVSEP_REQUIRE(B >= 0 && B <= 65535 && P >= 1, "avsep_pit_backward: bad B / P");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 256), B);
+  switch (S) {
+    case 1: pit_bwd_kernel<1><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
+    case 2: pit_bwd_kernel<2><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
+    case 3: pit_bwd_kernel<3><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
+    default: pit_bwd_kernel<4><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
+  }
+  AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
 

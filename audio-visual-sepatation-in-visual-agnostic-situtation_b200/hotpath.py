@@ -173,6 +173,55 @@ def calc_metrics(batch_data, outputs, args, get_metrics: Optional[Callable] = No
 
 
 # ------------------------------------------------------------------------------------------------
+# long-clip separation (BASELINE.json config C4)
+# ------------------------------------------------------------------------------------------------
+def clip_windows(audio: torch.Tensor, win: int = 65535, stride: int = 65535) -> torch.Tensor:
+    """Cut a long clip [..., L] into windows [..., W, win]; the tail window is zero-padded, as the reference pads
+    short clips (dataset/base.py:157-162).  The reference itself only ever processes one 6 s window
+    (inference.py:197-228); this is the defined extension to 60 s clips."""
+    L = audio.shape[-1]
+    W = max(1, -(-max(L - win, 0) // stride) + 1)
+    need = (W - 1) * stride + win
+    if need > L:
+        audio = torch.nn.functional.pad(audio, (0, need - L))
+    return audio.unfold(-1, win, stride).contiguous()
+
+
+def assemble_windows(wavs: torch.Tensor, stride: int, total_len: int) -> torch.Tensor:
+    """Inverse of clip_windows for reconstructed windows [W, ..., Lw] -> [..., total_len]: window i supplies the
+    samples [i*stride, i*stride + min(stride, Lw)), the last window everything it has; no cross-fade (the
+    reference defines none).  Positions no window reconstructs (Lw = 65280 < stride = 65535) stay zero."""
+    W, Lw = wavs.shape[0], wavs.shape[-1]
+    out = wavs.new_zeros(wavs.shape[1:-1] + (total_len,))
+    for i in range(W):
+        n = Lw if i == W - 1 else min(stride, Lw)
+        lo = i * stride
+        hi = min(lo + n, total_len)
+        if hi > lo:
+            out[..., lo:hi] = wavs[i][..., :hi - lo]
+    return out
+
+
+def separate_long_clip(audio_mix: torch.Tensor, mask_fn: Callable, *, win: int = 65535, stride: int = 65535,
+                       log_freq: bool = True, binary_mask: bool = True, mask_thres: float = 0.5,
+                       rank: int = 0, world: int = 1) -> torch.Tensor:
+    """Separate a long mixture [L] window by window on this rank's share of the windows.
+
+    mask_fn(log_mag_mix [W,1,256,T], mag_mix_w [W,1,256,T]) -> masks [N, W, 256, T] (the model: U-Net + synthesizer).
+    The STFT, warp and log of every window are computed once (the reference's vis_video recomputes them for each
+    video frame, inference.py:557-563).  Returns this rank's reconstructed windows [W_local, N+1, 256 (T-1)];
+    use parallel.gather_windows + assemble_windows to put the clip back together."""
+    windows = clip_windows(audio_mix.reshape(-1), win, stride)
+    mine = list(range(rank, windows.shape[0], world))
+    w = windows[mine].contiguous()
+    mag, _, re, im = ops.stft(w, phase=False, complex_parts=True)
+    _, mix_w, log_mix, _, _ = ops.prepare(mag[:, None], [], log_freq=log_freq, weighted_loss=False, binary_mask=binary_mask)
+    masks = mask_fn(log_mix, mix_w)
+    return ops.separate(masks, None, None, re_mix=re, im_mix=im, log_freq=log_freq, binary_mask=binary_mask,
+                        mask_thres=mask_thres, include_mix=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # fused end-to-end steps (what bench.py measures)
 # ------------------------------------------------------------------------------------------------
 class _DevView:

@@ -118,24 +118,15 @@ class BCELoss(BaseLoss):
 class PitWrapper(nn.Module):
     """models/criterion.py:74-231 with base_loss = F.binary_cross_entropy (models/__init__.py:130-131).
 
-    The S x S loss matrix of every sample is computed by one kernel over the whole batch (the
-    reference loops over samples and materialises [H,W,S,S] repeats); the S! permutation search
-    runs on the tiny [B,S,S] result.  Forward value and permutations match the reference; the
-    returned loss is not yet differentiable (PIT training is SURVEY.md section 8(f) rank 2, next round).
-    """
+    forward(preds [B,...,S], targets, weights) -> (loss [B], perms): the S x S loss matrix of every sample is
+    computed by one kernel over the whole batch (the reference loops over samples and materialises [H,W,S,S]
+    repeats), the S! search runs on the tiny [B,S,S] result, and the gradient flows back to `preds` through one
+    streaming kernel.  `base_loss` may be the string 'bce' / 'l1' / 'l2' or F.binary_cross_entropy (as the
+    reference passes it)."""
 
     def __init__(self, base_loss="bce"):
         super(PitWrapper, self).__init__()
         self.kind = base_loss if isinstance(base_loss, str) else "bce"
-
-    def _fast_pit(self, loss_mat):
-        loss, assigned = None, None
-        S = loss_mat.shape[0]
-        for p in permutations(range(S)):
-            c_loss = loss_mat[range(S), p].mean()
-            if loss is None or loss > c_loss:
-                loss, assigned = c_loss, p
-        return loss, assigned
 
     def reorder_tensor(self, tensor, p):
         idx = torch.as_tensor(p, device=tensor.device, dtype=torch.long)           # [B, S]
@@ -145,10 +136,4 @@ class PitWrapper(nn.Module):
     def forward(self, preds, targets, weights=None):
         if weights is None:
             weights = torch.ones_like(preds)
-        lm = ops.pit_lossmat(self.kind, preds, targets, weights).cpu()
-        losses, perms = [], []
-        for b in range(lm.shape[0]):
-            l, p = self._fast_pit(lm[b])
-            losses.append(l)
-            perms.append(p)
-        return torch.stack(losses).to(preds.device), perms
+        return ops.pit_loss(self.kind, preds, targets, weights)

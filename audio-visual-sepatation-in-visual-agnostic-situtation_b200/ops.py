@@ -498,3 +498,64 @@ def pit_lossmat(kind: str, preds: torch.Tensor, targets: torch.Tensor, weights: 
     check(lib.avsep_pit_lossmat(LOSS_KINDS[kind], p.data_ptr(), t.data_ptr(), w.data_ptr(), B, P, S, out.data_ptr(), _stream()),
           "avsep_pit_lossmat")
     return out
+
+
+def _pit_search(lossmat_host: torch.Tensor):
+    """Brute-force permutation search of PitWrapper._fast_pit (criterion.py:113-136) on the host [B,S,S] matrix:
+    itertools order, first minimum wins.  Returns (losses, perms, inverse perms)."""
+    from itertools import permutations
+    B, S = lossmat_host.shape[0], lossmat_host.shape[1]
+    idx = list(range(S))
+    losses, perms, inv = [], [], []
+    for b in range(B):
+        best, best_p = None, None
+        for perm in permutations(idx):
+            c = lossmat_host[b, idx, list(perm)].mean()
+            if best is None or best > c:
+                best, best_p = c, perm
+        losses.append(float(best))
+        perms.append(best_p)
+        ip = [0] * S
+        for i, j in enumerate(best_p):
+            ip[j] = i
+        inv.append(ip)
+    return losses, perms, inv
+
+
+class _PitLoss(torch.autograd.Function):
+    """Carries the gradient of loss[b] = mean_i lossmat[b][i][perm_b[i]] back to preds (one streaming kernel)."""
+
+    @staticmethod
+    def forward(ctx, kind, preds, targets, weights, inv_perm, loss_values):
+        ctx.kind = kind
+        ctx.save_for_backward(preds, targets, weights, inv_perm)
+        return loss_values.clone()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        p, t, w, inv = ctx.saved_tensors
+        B, S = p.shape[0], p.shape[-1]
+        P = p[0].numel() // S
+        g = _cuda_f32(gloss.reshape(B), "pit backward: grad")
+        dp = torch.empty_like(p)
+        check(lib.avsep_pit_backward(LOSS_KINDS[ctx.kind], p.data_ptr(), t.data_ptr(), w.data_ptr(), inv.data_ptr(), g.data_ptr(),
+                                     B, P, S, dp.data_ptr(), _stream()), "avsep_pit_backward")
+        return None, dp, None, None, None, None
+
+
+def pit_loss(kind: str, preds: torch.Tensor, targets: torch.Tensor, weights: torch.Tensor):
+    """PitWrapper.forward (criterion.py:202-231): returns (loss [B], differentiable in preds; perms list of tuples).
+
+    The S x S loss matrix of every sample comes from one kernel; the S! search runs on the host [B,S,S] result."""
+    p = _cuda_f32(preds, "pit: preds")
+    t = _cuda_f32(targets, "pit: targets")
+    w = _cuda_f32(weights, "pit: weights")
+    lm = pit_lossmat(kind, p, t, w)
+    losses, perms, inv = _pit_search(lm.double().cpu())
+    inv_t = torch.tensor(inv, dtype=torch.int32, device=p.device)
+    loss_t = torch.tensor(losses, dtype=torch.float32, device=p.device)
+    if preds.requires_grad and torch.is_grad_enabled():
+        if preds.data_ptr() != p.data_ptr():                         # preds was copied (non-contiguous / unaligned): keep the graph
+            return _PitLoss.apply(kind, preds.contiguous(), t, w, inv_t, loss_t), perms
+        return _PitLoss.apply(kind, preds, t, w, inv_t, loss_t), perms
+    return loss_t, perms

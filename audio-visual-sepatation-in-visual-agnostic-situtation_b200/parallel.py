@@ -79,3 +79,21 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t[0])
+
+
+def gather_windows(local: torch.Tensor, num_windows: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """Long-clip separation (config C4): every rank reconstructed the windows rank, rank + world, ... ;
+    returns all `num_windows` windows in order on every rank.  The one place tensors cross GPUs (waveforms out)."""
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return local
+    per = -(-num_windows // world)
+    pad = local.new_zeros((per,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = local.new_zeros((num_windows,) + tuple(local.shape[1:]))
+    for r in range(world):
+        idx = list(range(r, num_windows, world))
+        if idx:
+            out[idx] = bufs[r][:len(idx)]
+    return out

@@ -195,6 +195,12 @@ int avsep_scale_if_needed(float* x_dev, size_t n, const float* gscale_dev, void*
 int avsep_pit_lossmat(int loss_kind, const float* preds_dev, const float* targets_dev,
                       const float* weights_dev, int B, size_t P, int S, float* lossmat_dev, void* stream);
 
+/* Backward of the PIT loss  loss[b] = (1/S) sum_i lossmat[b][i][perm_b[i]]  w.r.t. preds:
+ *   inv_perm_dev [B, S] int32: inv_perm[b][j] = the target index matched with prediction j;  gloss_dev [B]. */
+int avsep_pit_backward(int loss_kind, const float* preds_dev, const float* targets_dev, const float* weights_dev,
+                       const int* inv_perm_dev, const float* gloss_dev, int B, size_t P, int S, float* dpreds_dev,
+                       void* stream);
+
 /* ---- end-to-end host-buffer entry points (what bench.py's `e2e` times) --------------------- */
 /* Config C2 train step through host buffers: H2D of the waveforms, STFT of all (N+1) signals,
  * prepare, synth + sigmoid + weighted BCE, full backward, D2H of the loss.

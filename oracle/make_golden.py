@@ -210,13 +210,18 @@ def main():
         # make sample 1 a permuted copy so the optimum is non-identity
         pr[1] = np.clip(tg[1][..., ::-1] * 0.9 + 0.05, 0.01, 0.99)
         ww = np.repeat(np.abs(g.standard_normal((3, 12, 10, 1))).astype(np.float32), S, axis=-1)
-        loss, perms = pitw(torch.from_numpy(pr), torch.from_numpy(tg), torch.from_numpy(ww))
+        tpr = torch.from_numpy(pr).requires_grad_(True)
+        loss, perms = pitw(tpr, torch.from_numpy(tg), torch.from_numpy(ww))
+        (loss * torch.tensor([1.0, 2.0, 0.5])).sum().backward()
         ol, op = O.pit("bce", pr, tg, ww)
         assert [tuple(p) for p in perms] == [tuple(p) for p in op], (perms, op)
-        report[f"pit_S{S}"] = relerr(ol, loss.numpy())
+        report[f"pit_S{S}"] = relerr(ol, loss.detach().numpy())
         re = pitw.reorder_tensor(torch.from_numpy(pr), perms).numpy()
         assert np.array_equal(re, O.pit_reorder(pr, op))
-        pit_out.update({f"S{S}_loss": loss.numpy(), f"S{S}_perms": np.asarray(perms, dtype=np.int64)})
+        og = O.pit_grad("bce", pr, tg, ww, op, np.array([1.0, 2.0, 0.5]))
+        report[f"pit_S{S}_grad"] = relerr(og, tpr.grad.numpy())
+        pit_out.update({f"S{S}_loss": loss.detach().numpy(), f"S{S}_perms": np.asarray(perms, dtype=np.int64),
+                        f"S{S}_grad": tpr.grad.numpy()})
     np.savez_compressed(os.path.join(OUT, "pit.npz"), **pit_out)
 
     # ---- 6. STFT / iSTFT (torch.stft = librosa stand-in) ----------------------------------------

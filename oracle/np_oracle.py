@@ -411,6 +411,28 @@ def pit(kind: str, preds, targets, weights):
     return np.asarray(losses), perms
 
 
+def pit_grad(kind: str, preds, targets, weights, perms, gloss):
+    """Gradient of sum_b gloss[b] * pit_loss[b] w.r.t. preds (autograd of criterion.py:159-176 with the chosen
+    permutation): prediction j is matched with target i where perms[b][i] == j."""
+    preds = np.asarray(preds, dtype=np.float64)
+    targets = np.asarray(targets, dtype=np.float64)
+    weights = np.asarray(weights, dtype=np.float64)
+    B, S = preds.shape[0], preds.shape[-1]
+    P = preds[0].size // S
+    out = np.zeros_like(preds)
+    for b in range(B):
+        for i, j in enumerate(perms[b]):
+            p, t, w = preds[b][..., j], targets[b][..., i], weights[b][..., i]
+            if kind == "bce":
+                g = w * (p - t) / np.maximum(p * (1 - p), 1e-12)
+            elif kind == "l1":
+                g = w * np.sign(p - t)
+            else:
+                g = w * 2 * (p - t)
+            out[b][..., j] = gloss[b] * g / (S * P)
+    return out
+
+
 def pit_reorder(tensor, perms):
     """PitWrapper.reorder_tensor (criterion.py:180-200): out[b] = tensor[b][..., perms[b]]."""
     out = np.zeros_like(tensor)

@@ -105,3 +105,22 @@ def test_warpgrid_compat(golden):
     gw = av.warpgrid(2, 256, 256, warp=True)
     assert gw.shape == (2, 256, 256, 2) and gw.dtype == np.float32
     assert np.array_equal(gw[1, :, 5, 1], g["warp_y"]) and np.array_equal(gw[0, 3, :, 0], g["warp_x"])
+
+
+def test_clip_windows_and_assemble_roundtrip():
+    """Long-clip helper (config C4): 60 s @ 11025 Hz -> windows; stride 65535 -> 11 windows, stride 32768 -> 20."""
+    L = 661500
+    x = torch.arange(L, dtype=torch.float32)
+    w = av.clip_windows(x, 65535, 65535)
+    assert w.shape == (11, 65535) and float(w[10, -1]) == 0.0 and float(w[1, 0]) == 65535.0
+    assert av.clip_windows(x, 65535, 32768).shape[0] == 20
+    assert av.clip_windows(x[:1000], 65535, 65535).shape == (1, 65535)
+    # reconstruction windows are 65280 long: assemble puts each at its offset, gaps of 255 samples stay zero
+    rec = w[:, :65280]
+    y = av.assemble_windows(rec, 65535, L)
+    assert torch.equal(y[:65280], x[:65280]) and float(y[65280:65535].abs().max()) == 0.0
+    assert torch.equal(y[65535:65535 + 65280], x[65535:65535 + 65280])
+    # overlapping stride: later windows take over at their offset
+    w2 = av.clip_windows(x, 65535, 32768)
+    y2 = av.assemble_windows(w2[:, :65280], 32768, L)
+    assert torch.equal(y2[:L - 300], x[:L - 300])

@@ -320,8 +320,11 @@ def test_pit_matches_reference_golden(golden):
         tg = (r.random((3, 12, 10, S)) > 0.5).astype(np.float32)
         pr[1] = np.clip(tg[1][..., ::-1] * 0.9 + 0.05, 0.01, 0.99)
         ww = np.repeat(np.abs(r.standard_normal((3, 12, 10, 1))).astype(np.float32), S, axis=-1)
-        loss, perms = pw(_cuda(pr), _cuda(tg), _cuda(ww))
-        assert relerr(loss.cpu().numpy(), g[f"S{S}_loss"]) < 1e-5
+        tpr = _cuda(pr).requires_grad_(True)
+        loss, perms = pw(tpr, _cuda(tg), _cuda(ww))
+        (loss * torch.tensor([1.0, 2.0, 0.5], device="cuda")).sum().backward()
+        assert relerr(tpr.grad.cpu().numpy(), g[f"S{S}_grad"]) < 1e-5
+        assert relerr(loss.detach().cpu().numpy(), g[f"S{S}_loss"]) < 1e-5
         assert np.array_equal(np.asarray(perms), g[f"S{S}_perms"])
         re = pw.reorder_tensor(_cuda(pr), perms).cpu().numpy()
         assert np.array_equal(re, O.pit_reorder(pr, perms))

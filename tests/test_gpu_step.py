@@ -186,3 +186,63 @@ def test_n3_and_batch_shapes():
         for n in range(N):
             assert np.max(np.abs(got[:, 1 + n] - pred_o[:, n])) / s < TOL
         st.close()
+
+
+def test_long_clip_windows_vs_oracle():
+    """Config C4 (small): a 3-window clip, fixed masks; every window equals the oracle's single-window path."""
+    rng = np.random.default_rng(3)
+    L_long = 65535 * 2 + 20000
+    src = O.synth_sources(1, 1, L=L_long, seed=11)[0, 0]
+    masks_np = rng.random((2, 3, 256, 256)).astype(np.float32)
+    seen = {}
+
+    def mask_fn(log_mix, mix_w):
+        seen["shape"] = tuple(log_mix.shape)
+        return torch.from_numpy(masks_np).cuda()
+
+    out = av.separate_long_clip(torch.from_numpy(src).cuda(), mask_fn, binary_mask=False)
+    assert seen["shape"] == (3, 1, 256, 256) and out.shape == (3, 3, 65280)
+    wins = av.clip_windows(torch.from_numpy(src), 65535, 65535).numpy()
+    for i in range(3):
+        amp, ph = O.stft_magphase(wins[i])
+        mix_o, pred_o, _ = O.separate(amp[None, None], ph[None, None], [masks_np[n][i][None, None] for n in range(2)], binary_mask=False)
+        s = max(np.max(np.abs(mix_o)), 1e-9)
+        got = out[i].cpu().numpy()
+        assert np.max(np.abs(got[0] - mix_o[0])) / s < TOL
+        assert np.max(np.abs(got[1:] - pred_o[0])) / s < TOL
+    full = av.assemble_windows(out[:, 0], 65535, L_long).cpu().numpy()
+    assert np.max(np.abs(full[:65280] - src[:65280])) < 1e-4
+
+
+def test_full_size_c3_and_c5_properties():
+    """Size-independent properties at BASELINE sizes.  C3: B = 128, N = 3 eval shapes -- with masks that sum to one
+    on the linear axis the separated sources add up to the mixture reconstruction (linearity of mask * iSTFT).
+    C5: a B = 256 synthesizer batch made of 8 distinct mixtures tiled 32x gives the loss and the tiled gradients
+    of the B = 8 batch."""
+    B, N = 128, 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    mix = (torch.rand((B, L), device="cuda", generator=g) - 0.5) * 0.5
+    mag, _, re, im = av.stft(mix, phase=False, complex_parts=True)
+    m = torch.rand((N, B, 512, 256), device="cuda", generator=g)
+    m = m / m.sum(dim=0, keepdim=True)
+    wav = av.separate(m, None, None, re_mix=re, im_mix=im, log_freq=False, binary_mask=False)
+    assert wav.shape == (B, N + 1, 65280)
+    err = float((wav[:, 1:].sum(dim=1) - wav[:, 0]).abs().max())
+    assert err < 2e-5, err
+    assert float((wav[:, 0] - mix[:, :65280]).abs().max()) < 2e-5          # and the mixture itself round-trips
+    del wav, m, mag, re, im
+    K, rep = 32, 32
+    feat8 = torch.randn((8, K, 256, 256), device="cuda", generator=g)
+    vec8 = torch.sigmoid(torch.randn((8, 2, K), device="cuda", generator=g))
+    gt8 = (torch.rand((2, 8, 256, 256), device="cuda", generator=g) > 0.5).float()
+    w8 = torch.rand((8, 1, 256, 256), device="cuda", generator=g) + 0.1
+    net = av.InnerProd(K).cuda()
+    f8 = feat8.clone().requires_grad_(True)
+    e8, _ = net.forward_loss(vec8, f8, gt8, w8)
+    e8.backward()
+    fb = feat8.repeat(rep, 1, 1, 1).requires_grad_(True)
+    eb, _ = net.forward_loss(vec8.repeat(rep, 1, 1), fb, gt8.repeat(1, rep, 1, 1), w8.repeat(rep, 1, 1, 1))
+    eb.backward()
+    assert abs(float(eb.detach()) - float(e8.detach())) < 1e-6 * abs(float(e8.detach()))
+    assert float((fb.grad[:8] * rep - f8.grad).abs().max()) <= 1e-6 * float(f8.grad.abs().max())
+    assert torch.equal(fb.grad[:8], fb.grad[8 * (rep - 1):])

@@ -120,6 +120,7 @@ def test_pit_matches_reference(golden):
         assert relerr(loss, g[f"S{S}_loss"]) < TOL
         assert np.array_equal(np.asarray(perms), g[f"S{S}_perms"])
         assert tuple(perms[1]) != tuple(range(S))
+        assert relerr(O.pit_grad("bce", pr, tg, ww, perms, np.array([1.0, 2.0, 0.5])), g[f"S{S}_grad"]) < TOL
 
 
 def test_pit_doctest_property():

@@ -30,6 +30,12 @@ def _worker(rank, world, port, total, q):
     sums = dict(sdr=float(local.sum()), sir=float((2 * local).sum()))
     m = parallel.global_metrics(sums, hi - lo)
     mx = parallel.max_over_ranks(float(rank + 1))
+    # long-clip windows: rank r owns windows r, r + world, ...; every rank ends up with all of them, in order
+    nw = 5
+    mine = parallel.shard_windows(nw, rank, world)
+    local = torch.stack([torch.full((2, 3), float(i)) for i in mine])
+    allw = parallel.gather_windows(local, nw, rank, world)
+    assert allw.shape == (nw, 2, 3) and [float(allw[i, 0, 0]) for i in range(nw)] == [0.0, 1.0, 2.0, 3.0, 4.0]
     q.put((rank, lo, hi, float(g), m, mx))
     dist.barrier()
     dist.destroy_process_group()
