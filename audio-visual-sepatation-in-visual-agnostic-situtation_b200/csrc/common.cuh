@@ -115,6 +115,12 @@ __device__ __forceinline__ float fast_log1p_pos(float x) {
   return __logf(1.f + x);
 }
 
+// log(1 - p) for p in [0, 1]: series below 2^-5, log(1 - p) above (1 - p is exact for p >= 0.5); p == 1 -> -inf
+__device__ __forceinline__ float fast_log1m(float p) {
+  if (p < 0.03125f) return -p * (1.f + p * (0.5f + p * (0.33333334f + p * 0.25f)));
+  return __logf(1.f - p);
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");

@@ -326,7 +326,27 @@ constexpr int SYN_TR_THREADS = 128;
 constexpr int SYN_TR_GROUPS = 4;                       // pixel groups of 128 x 4 px walked by one CTA
 constexpr int SYN_TR_SMEM = 32 * SYN_TR_THREADS * 16;  // 64 KB staging
 
-template <int NS>
+// fused-kernel variants of the loss element / gradient: same formulas, MUFU-based logs (3 ulp) and, for
+// sigmoid + BCE, the closed form of torch's two-step gradient
+//   (p - t) / max(p (1 - p), 1e-12) * p (1 - p)  ==  (p - t) * min(1, p (1 - p) * 1e12)
+// which keeps the exact zero where the float32 sigmoid saturates.
+__device__ __forceinline__ float loss_elem_fast(int kind, float p, float t) {
+  if (kind == AVSEP_LOSS_BCE) {
+    const float lp = fmaxf(fast_log(p), -100.f);
+    const float l1p = fmaxf(fast_log1m(p), -100.f);
+    return (t - 1.f) * l1p - t * lp;
+  }
+  const float d = p - t;
+  return kind == AVSEP_LOSS_L1 ? fabsf(d) : d * d;
+}
+__device__ __forceinline__ float dz_elem_fast(int kind, int act, float p, float t) {
+  if (kind == AVSEP_LOSS_BCE && act == AVSEP_ACT_SIGMOID) return (p - t) * fminf(1.f, (1.f - p) * p * 1e12f);
+  float d = loss_grad(kind, p, t);
+  if (act == AVSEP_ACT_SIGMOID) d *= (1.f - p) * p;
+  return d;
+}
+
+template <int NS, bool FULLK>
 __global__ void __launch_bounds__(SYN_TR_THREADS, (NS <= 2 ? 3 : 2))
 synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
                    const float* __restrict__ bias, int B, int K, int HW, int act, int loss_kind, const float* __restrict__ gt,
@@ -365,7 +385,7 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
     //      (no staging registers, 32 loads in flight per thread) ----------------------------------------------------
 #pragma unroll
     for (int k = 0; k < SYN_KCHUNK; ++k)
-      if (k < K) cp_async_16(&stage[k * SYN_TR_THREADS + tid], fbase + (size_t)k * HW + px);
+      if (FULLK || k < K) cp_async_16(&stage[k * SYN_TR_THREADS + tid], fbase + (size_t)k * HW + px);
     cp_async_commit();
     // small streams overlap the feat loads
     float w[4] = {1.f, 1.f, 1.f, 1.f};
@@ -385,7 +405,7 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
       for (int e = 0; e < 4; ++e) z[n][e] = 0.f;
 #pragma unroll
     for (int k = 0; k < SYN_KCHUNK; ++k) {
-      if (k < K) {
+      if (FULLK || k < K) {
         const float4 f = stage[k * SYN_TR_THREADS + tid];
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
@@ -406,11 +426,10 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
       float pr[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        pr[e] = act_apply(act, z[n][e] + bz);
-        lsum += w[e] * loss_elem(loss_kind, pr[e], tt[e]);
-        float d = g * w[e] * loss_grad(loss_kind, pr[e], tt[e]);
-        if (act == AVSEP_ACT_SIGMOID) d *= (1.f - pr[e]) * pr[e];
-        dz[n][e] = d;
+        const float zz = z[n][e] + bz;
+        pr[e] = act == AVSEP_ACT_SIGMOID ? __frcp_rn(1.0f + expf(-zz)) : zz;     // == 1 / (1 + exp(-z)), correctly rounded
+        lsum += w[e] * loss_elem_fast(loss_kind, pr[e], tt[e]);
+        dz[n][e] = g * w[e] * dz_elem_fast(loss_kind, act, pr[e], tt[e]);
       }
       *reinterpret_cast<float4*>(pred + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);
       dzs[n] += (dz[n][0] + dz[n][1]) + (dz[n][2] + dz[n][3]);
@@ -418,7 +437,7 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
     // ---- pass 2: dfeat out, S accumulation from the parked feat ------------------------------------------------
 #pragma unroll
     for (int k = 0; k < SYN_KCHUNK; ++k) {
-      if (k < K) {
+      if (FULLK || k < K) {
         const float4 f = stage[k * SYN_TR_THREADS + tid];
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -428,7 +447,12 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
           o4.y = fmaf(c, dz[n][1], o4.y);
           o4.z = fmaf(c, dz[n][2], o4.z);
           o4.w = fmaf(c, dz[n][3], o4.w);
-          S[n][k] += (dz[n][0] * f.x + dz[n][1] * f.y) + (dz[n][2] * f.z + dz[n][3] * f.w);
+          float acc = S[n][k];
+          acc = fmaf(dz[n][0], f.x, acc);
+          acc = fmaf(dz[n][1], f.y, acc);
+          acc = fmaf(dz[n][2], f.z, acc);
+          acc = fmaf(dz[n][3], f.w, acc);
+          S[n][k] = acc;
         }
         st_stream(reinterpret_cast<float4*>(dbase + (size_t)k * HW + px), o4);
       }
@@ -608,7 +632,7 @@ static int synth_train_n(const float* feat, const float* vecs, const float* scal
   float* dz_partial = reinterpret_cast<float*>(sc + lay.dz_partial);
   const int chunks = ceil_div(HW, SYN_TR_THREADS * 4 * SYN_TR_GROUPS);      // == lay.bwd_chunks (same 2048 px per CTA)
   static_assert(SYN_TR_THREADS * SYN_TR_GROUPS == SYN_BWD_THREADS * SYN_BWD_ITERS, "scratch layout shared with the backward kernel");
-  auto kern = synth_train_kernel<NS>;
+  auto kern = (K == SYN_KCHUNK) ? synth_train_kernel<NS, true> : synth_train_kernel<NS, false>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_TR_SMEM));
   dim3 grid(chunks, B);
   const float inv_count = (float)(1.0 / ((double)B * (double)HW * (double)NS));
