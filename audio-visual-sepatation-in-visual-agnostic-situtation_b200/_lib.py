@@ -79,6 +79,7 @@ SIGNATURES = {
     "avsep_step_plan": (_P, [_P]),
     "avsep_step_set_mix_on_device": (_I, [_P, _I]),
     "avsep_step_set_fused_train": (_I, [_P, _I]),
+    "avsep_step_set_graph": (_I, [_P, _I]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -4,6 +4,7 @@
 // Host-buffer variants add the H2D copy of the waveforms / K-vectors and the D2H copy of the result
 // inside the call.  feat_sound is the U-Net's output in the reference and never exists on the host
 // there, so it stays a device pointer.
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -33,6 +34,10 @@ struct avsep_step {
   int B = 0, N = 0, K = 0, L = 0, T = 0, HW = 0, out_len = 0;
   int mix_on_device = 0;      // waves arguments hold only the N sources; the mixture is summed on the GPU
   int no_fused_train = 0;     // debugging / A-B timing: run the separate forward and backward kernels
+  int use_graph = 0;          // replay the train step as a CUDA graph (non-default streams only)
+  cudaGraphExec_t graph_exec = nullptr;
+  const void* graph_key[12] = {};
+  int graph_launches = 0;
   avsep_plan* plan = nullptr;
   float* waves = nullptr;     // [N+1, B, L]  (index 0 = mixture)
   float* vecs = nullptr;      // [B, N, K]
@@ -83,6 +88,7 @@ extern "C" {
 
 int avsep_step_destroy(avsep_step* st) {
   if (!st) return AVSEP_OK;
+  if (st->graph_exec) cudaGraphExecDestroy(st->graph_exec);
   avsep_plan_destroy(st->plan);
   float* bufs[] = {st->waves, st->vecs, st->mag, st->mix_re, st->mix_im, st->mix_w, st->log_mix, st->weights, st->mags_w,
                    st->gt, st->pred, st->loss, st->one, st->dvecs, st->dscale, st->dbias, st->wav};
@@ -131,11 +137,9 @@ int avsep_step_create(avsep_step** step, int B, int N, int K, int wave_len) {
   return AVSEP_OK;
 }
 
-int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
-                         const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
-                         float* dbias_dev, float* loss_dev, void* stream_) {
-  AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_train_dev: null argument");
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int train_dev_body(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
+                          const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
+                          float* dbias_dev, float* loss_dev, cudaStream_t stream) {
   const bool fused = dfeat_dev != nullptr && synth_train_supported(st->K, st->HW, dfeat_dev) && !st->no_fused_train;
   int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, false, stream, !fused);
   if (rc) return rc;
@@ -149,6 +153,65 @@ int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* ve
                            dscale_dev ? dscale_dev : st->dscale, dbias_dev ? dbias_dev : st->dbias, st->scratch, stream);
   if (rc) return rc;
   if (loss_dev) AVSEP_CUDA(cudaMemcpyAsync(loss_dev, st->loss, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  return AVSEP_OK;
+}
+
+// The train step is a fixed sequence of 6 kernels + 1 copy.  With graphs enabled the sequence is captured once per
+// argument tuple (on its second call, after the lazily-created tap tables exist) and replayed with one
+// cudaGraphLaunch, which removes the per-kernel launch gaps (~7 % of a 0.65 ms step).
+int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
+                         const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
+                         float* dbias_dev, float* loss_dev, void* stream_) {
+  AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_train_dev: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!st->use_graph || stream == nullptr || stream == cudaStreamLegacy || stream == cudaStreamPerThread)
+    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
+  const void* key[12] = {waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev,
+                         (const void*)(uintptr_t)(st->mix_on_device * 2 + st->no_fused_train), (const void*)stream};
+  if (st->graph_exec && memcmp(key, st->graph_key, sizeof(key)) == 0) {
+    AVSEP_CUDA(cudaGraphLaunch(st->graph_exec, stream));
+    count_launch(st->graph_launches);
+    return AVSEP_OK;
+  }
+  if (memcmp(key, st->graph_key, sizeof(key)) != 0) {      // first call with these arguments: run directly (warm-up)
+    memcpy(st->graph_key, key, sizeof(key));
+    if (st->graph_exec) { cudaGraphExecDestroy(st->graph_exec); st->graph_exec = nullptr; }
+    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
+  }
+  // second call with the same arguments: capture, instantiate, launch
+  const uint64_t before = avsep_launch_count();
+  AVSEP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  int rc = train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+  if (rc || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    st->use_graph = 0;                                     // capture is not possible here: fall back to plain launches
+    if (rc) return rc;
+    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
+  }
+  ce = cudaGraphInstantiate(&st->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    st->graph_exec = nullptr;
+    st->use_graph = 0;
+    cudaGetLastError();
+    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
+  }
+  st->graph_launches = (int)(avsep_launch_count() - before);
+  AVSEP_CUDA(cudaGraphLaunch(st->graph_exec, stream));
+  return AVSEP_OK;
+}
+
+int avsep_step_set_graph(avsep_step* st, int enable) {
+  AVSEP_REQUIRE(st != nullptr, "avsep_step_set_graph: step is null");
+  st->use_graph = enable ? 1 : 0;
+  if (!enable && st->graph_exec) {
+    cudaGraphExecDestroy(st->graph_exec);
+    st->graph_exec = nullptr;
+    memset(st->graph_key, 0, sizeof(st->graph_key));
+  }
   return AVSEP_OK;
 }
 

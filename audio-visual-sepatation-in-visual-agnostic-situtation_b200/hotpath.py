@@ -245,6 +245,10 @@ class Step:
         self.T = 1 + wave_len // ops.HOP
         self.out_len = ops.HOP * (self.T - 1)
 
+    def set_graph(self, enable: bool = True):
+        """Replay the train step as a CUDA graph (captured on the 2nd call with unchanged arguments; side streams only)."""
+        check(lib.avsep_step_set_graph(self._h, int(bool(enable))), "avsep_step_set_graph")
+
     def set_fused_train(self, enable: bool = True):
         """False: run the separate synthesizer forward / backward kernels instead of the fused training kernel."""
         check(lib.avsep_step_set_fused_train(self._h, int(bool(enable))), "avsep_step_set_fused_train")

@@ -48,6 +48,9 @@ ALG = {
     "prepare": dict(bound="hbm", bytes=1572864 + 786432 + 1048576),            # warp in + out + derived out
     # fused forward + loss + backward: feat_sound in (once), dfeat out, masks out, gt + weight in, K-vectors
     "synth_train": dict(bound="hbm", bytes=8388864 + 8388608 + 524288 + 524288 + 262144),
+    # eval-only kernels: un-warp in + (mix re, im) in -> bf16 hi/lo operand out (3 signals x 256 x 1024 x 2 x 2 B)
+    "spec_prep": dict(bound="hbm", bytes=524288 + 1048576 + 3 * 256 * 1024 * 4),
+    "dft_gemm_inv": dict(bound="tensor", flops=1.607e9),                       # 3 signals x 0.536 GFLOP
     # the unfused pair (reported for comparison only): SURVEY.md section 8(d) staged figures
     "synth_fwd_loss": dict(bound="hbm", bytes=8388864 + 524288 + 1310720),
     "synth_bwd": dict(bound="hbm", bytes=9699328 + 8388608),
@@ -246,7 +249,10 @@ def main_ours(args, rank, world, local):
     loss = torch.zeros(1, device=dev)
     dvecs_host = torch.empty((B, N, K)).pin_memory()
     step = av.Step(B, N, K, L)
+    step.set_graph(not args.no_graph)                              # train step replayed as a CUDA graph (side streams only)
     eval_mode = args.workload == "eval"
+    main_stream = torch.cuda.Stream()                              # graphs cannot be captured on the legacy default stream
+    torch.cuda.set_stream(main_stream)
     wav_dev = torch.empty((B, N + 1, 65280), device=dev) if eval_mode else None
     wav_host = torch.empty((B, N + 1, 65280)).pin_memory() if eval_mode else None
 
@@ -311,6 +317,7 @@ def main_ours(args, rank, world, local):
         pipe_depth = 1
     else:
         step_b = av.Step(B, N, K, L)
+        step_b.set_graph(not args.no_graph)
         pipes = [dict(step=step, stream=torch.cuda.Stream(), dfeat=dfeat, loss=torch.zeros(1).pin_memory(),
                       dvecs=torch.empty((B, N, K)).pin_memory()),
                  dict(step=step_b, stream=torch.cuda.Stream(), dfeat=torch.empty_like(feat), loss=torch.zeros(1).pin_memory(),
@@ -368,6 +375,35 @@ def main_ours(args, rank, world, local):
     # ---- per-kernel roofline (rank 0), each kernel timed alone with CUDA events ---------------------------
     kernels = []
     roofline = None
+    if rank == 0 and eval_mode:
+        lib, stream, chk = av._lib.lib, torch.cuda.current_stream().cuda_stream, av._lib.check
+        plan = lib.avsep_step_plan(step._h)
+        S = (N + 1) * B
+        mag = torch.empty((S, 512, T), device=dev)
+        re = torch.empty((B, 512, T), device=dev)
+        im = torch.empty((B, 512, T), device=dev)
+        pred = step.buffer("pred_masks")
+        t_stft = time_calls(lambda: chk(lib.avsep_stft(plan, waves_dev.data_ptr(), S, mag.data_ptr(), None, None, None, stream)), 10)
+        t_gemm = time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan, 0, S, mag.data_ptr(), stream)), 10)
+        step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        re.copy_(step.buffer("mix_re")); im.copy_(step.buffer("mix_im"))
+        t_sep = time_calls(lambda: chk(lib.avsep_separate(plan, pred.data_ptr(), N, B, None, None, re.data_ptr(), im.data_ptr(), 1, 1,
+                                                          0.5, 1, wav_dev.data_ptr(), stream)), 10)
+        t_inv = time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan, 1, S, wav_dev.data_ptr(), stream)), 10)
+        times = {"dft_gemm_fwd": t_gemm, "wave_split": max(t_stft - t_gemm, 1e-6), "spec_prep": max(t_sep - t_inv, 1e-6),
+                 "dft_gemm_inv": t_inv}
+        for name, ms in times.items():
+            a = ALG[name]
+            if a["bound"] == "tensor":
+                ach = a["flops"] * B / (ms * 1e-3) / 1e12
+                kernels.append(dict(kernel=name, ms=ms, bound="tensor", achieved=ach, peak=pk["tensor"], unit="TFLOP/s",
+                                    frac=ach / pk["tensor"], executed_tflops=3 * ach, tensor_pipe_frac=3 * ach / pk["tensor"]))
+            else:
+                ach = a["bytes"] * B / (ms * 1e-3) / 1e9
+                kernels.append(dict(kernel=name, ms=ms, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"]))
+        top = max(kernels, key=lambda k: k["ms"])
+        roofline = dict(kernel=top["kernel"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"],
+                        frac=top["frac"], traffic=None, peak_source=pk["source"])
     if rank == 0 and not eval_mode:
         lib, stream = av._lib.lib, torch.cuda.current_stream().cuda_stream
         plan = lib.avsep_step_plan(step._h)
@@ -443,6 +479,7 @@ def main_ours(args, rank, world, local):
                                   "C2 MUSIC N=2 train step: STFT(3 signals)+prepare+synth K=32+sigmoid+weighted BCE+backward"),
                         batch_per_gpu=B, global_batch=B * world, num_mix=N, K=K, samples=L, stft="1022/256", grid="256x256",
                         parallelism=f"batch-sharded x{world}, no data-path collective",
+                        launch=("plain launches" if args.no_graph or eval_mode else "CUDA graph replay of the 6-kernel step"),
                         l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                      pipeline_depth=pipe_depth, timer="host wall clock around the K steps, synchronised on both sides",
@@ -468,6 +505,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain kernel launches instead of CUDA-graph replay of the step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -81,6 +81,23 @@ def test_train_step_vs_oracle():
     dv_host = torch.empty((B, N, K)).pin_memory()
     lh = st.train_host(wh, vh, tfeat, c(scale), c(bias), dfeat2, dv_host)
     assert lh == float(loss) and torch.equal(dfeat, dfeat2) and torch.equal(dv_host.cuda(), dvecs)
+    # CUDA-graph replay of the step (side stream): same bits as the plain launches
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        st.set_graph(True)
+        dfeat_g = torch.empty_like(dfeat)
+        loss_g = torch.empty(1, device="cuda")
+        tw, tv, tsc, tb = c(waves), c(vecs), c(scale), c(bias)
+        before = av.launch_count()
+        for _ in range(4):                                         # call 1 direct, call 2 captures + launches, calls 3-4 replay
+            dfeat_g.zero_()
+            st.train_dev(tw, tv, tfeat, tsc, tb, dfeat_g, None, None, None, loss_g)
+        side.synchronize()
+        assert av.launch_count() - before == 4 * 5                 # wave_split, dft_gemm, prepare, synth_train, finalize per step
+        assert float(loss_g) == float(loss) and torch.equal(dfeat_g, dfeat)
+        st.set_graph(False)
+    torch.cuda.current_stream().wait_stream(side)
     # separate forward / backward kernels (two passes over feat_sound) agree with the fused training kernel
     st.set_fused_train(False)
     loss4 = torch.empty(1, device="cuda")
