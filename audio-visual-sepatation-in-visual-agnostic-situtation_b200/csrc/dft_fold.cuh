@@ -1,0 +1,225 @@
+// Forward STFT as a FOLDED split-precision tcgen05 GEMM: half the tensor work of dft_gemm.cuh.
+//
+// For a real frame x[0..1021] and the symmetric periodic Hann window w (w[n] = w[1022 - n]):
+//   Re X[f] =  sum_{n=0}^{511} w[n] cos(2 pi f n / 1022) * E[n],   E[n] = x[n] + x[1022 - n]  (E[0] = x[0], E[511] = x[511])
+//   Im X[f] = -sum_{n=1}^{510} w[n] sin(2 pi f n / 1022) * O[n],   O[n] = x[n] - x[1022 - n]  (O[0] = O[511] = 0)
+// so the 1024 x 1024 x T contraction per signal becomes two 512 x 512 x T ones (cos rows x E, sin rows x O).
+//
+// Tile = 128 bins x 256 frames; the Re accumulator lives in TMEM columns [0, 256), the Im accumulator in
+// [256, 512) of the SAME lanes, so an epilogue thread owns (re, im) of its bin without any exchange.  Both halves of
+// TMEM are used by one tile, so the epilogue is not overlapped with the next tile's MMAs; it is spread over 8
+// warps (2 per TMEM lane group) to keep it short (~7 % of the tile time).
+//   warp 0: TMA producer | warp 1: TMEM allocator + MMA issuer | warps 2..9: epilogue
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace avsep {
+
+constexpr int FOLD_K = 512;            // folded samples per frame
+constexpr int FOLD_BINS = 512;
+constexpr int FOLD_TILE_M = 128;
+constexpr int FOLD_TILE_N = 256;
+constexpr int FOLD_M_TILES = FOLD_BINS / FOLD_TILE_M;   // 4
+constexpr int FOLD_THREADS = 320;
+constexpr int FOLD_SMEM_LIMIT = 232448;
+
+template <int BK>
+struct FoldCfg {
+  static_assert(BK == 32 || BK == 64, "K block is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int A_BYTES = FOLD_TILE_M * ROW_BYTES;
+  static constexpr int B_BYTES = FOLD_TILE_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
+  static constexpr int KB_HALF = FOLD_K / BK;          // k-blocks per accumulator (Re, then Im)
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
+};
+
+struct FoldParams {
+  int num_signals;
+  int T;
+  int n_tiles;       // ceil(T / 256)
+  int total_tiles;   // S * n_tiles * 4
+  int s_cap;         // signals per (kind, split) plane of the staged operand
+  float* mag;        // [S, 512, T]
+  float* phase;      // optional
+  float* re;         // optional (with im), written for signals s < reim_count
+  float* im;
+  int reim_count;
+  int* err_flag;
+};
+
+// basis tensor map: rows = (kind * 2 + split) * 512 + f, cols = n (512)        kind 0 = cos, 1 = -sin
+// operand tensor map: dims (n = 512, t = T, plane = (kind * 2 + split) * s_cap + s)   kind 0 = E, 1 = O
+template <int BK>
+__global__ void __launch_bounds__(FOLD_THREADS, 1)
+dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FoldParams p) {
+  using Cfg = FoldCfg<BK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 256);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m = tile % FOLD_M_TILES;
+        const int rest = tile / FOLD_M_TILES;
+        const int nt = rest % p.n_tiles;
+        const int s = rest / p.n_tiles;
+        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
+          const int kind = kb / Cfg::KB_HALF;                 // 0: cos x E -> Re, 1: -sin x O -> Im
+          const int k0 = (kb % Cfg::KB_HALF) * BK;
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 11);
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(&tmA, full_bar(stage), st, k0, (kind * 2 + 0) * FOLD_BINS + m * FOLD_TILE_M);
+          tma_load_2d(&tmA, full_bar(stage), st + Cfg::A_BYTES, k0, (kind * 2 + 1) * FOLD_BINS + m * FOLD_TILE_M);
+          tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES, k0, nt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + s);
+          tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, nt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + s);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(FOLD_TILE_M, FOLD_TILE_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar, tile_phase ^ 1u, p.err_flag, 12);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
+          const int kind = kb / Cfg::KB_HALF;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(kind * FOLD_TILE_N);
+          const bool first = (kb % Cfg::KB_HALF) == 0;
+          mbar_wait(full_bar(stage), phase, p.err_flag, 13);
+          tcgen05_fence_after();
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = umma_smem_desc(st, Cfg::ROW_BYTES);
+          const uint64_t a_lo = umma_smem_desc(st + Cfg::A_BYTES, Cfg::ROW_BYTES);
+          const uint64_t b_hi = umma_smem_desc(st + 2 * Cfg::A_BYTES, Cfg::ROW_BYTES);
+          const uint64_t b_lo = umma_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::ROW_BYTES);
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t adv = (uint64_t)(k16 * 2);
+            umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, (first && k16 == 0) ? 0u : 1u);
+            umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+        tile_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue (8 warps) ================================
+    const int q = warp & 3;                 // TMEM lane group this warp may touch
+    const int half = (warp - 2) >> 2;       // which 128 of the 256 frame columns
+    uint32_t tile_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m = tile % FOLD_M_TILES;
+      const int rest = tile / FOLD_M_TILES;
+      const int nt = rest % p.n_tiles;
+      const int s = rest / p.n_tiles;
+      mbar_wait(tfull_bar, tile_phase, p.err_flag, 14);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int f = FOLD_TILE_M * m + 32 * q + lane;
+      const size_t row_off = ((size_t)s * AVSEP_N_BINS + f) * (size_t)p.T;
+      const bool vec_ok = (p.T & 3) == 0;
+      const bool want_reim = p.re != nullptr && s < p.reim_count;
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        const int t0 = nt * FOLD_TILE_N + c0;
+        if (t0 >= p.T) break;
+        uint32_t vr[32], vi[32];
+        tmem_ld_32x32b_x32(taddr + c0, vr);
+        tmem_ld_32x32b_x32(taddr + FOLD_TILE_N + c0, vi);
+        tmem_ld_wait();
+        if (vec_ok && t0 + 32 <= p.T) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float rr[4], ii[4], mg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              rr[e] = __uint_as_float(vr[j + e]);
+              ii[e] = __uint_as_float(vi[j + e]);
+              mg[e] = sqrtf(fmaf(rr[e], rr[e], ii[e] * ii[e]));
+            }
+            *reinterpret_cast<float4*>(p.mag + row_off + t0 + j) = make_float4(mg[0], mg[1], mg[2], mg[3]);
+            if (p.phase)
+              *reinterpret_cast<float4*>(p.phase + row_off + t0 + j) =
+                  make_float4(atan2f(ii[0], rr[0]), atan2f(ii[1], rr[1]), atan2f(ii[2], rr[2]), atan2f(ii[3], rr[3]));
+            if (want_reim) {
+              *reinterpret_cast<float4*>(p.re + row_off + t0 + j) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+              *reinterpret_cast<float4*>(p.im + row_off + t0 + j) = make_float4(ii[0], ii[1], ii[2], ii[3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (t0 + j < p.T) {
+              const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
+              p.mag[row_off + t0 + j] = sqrtf(fmaf(rr, rr, ii * ii));
+              if (p.phase) p.phase[row_off + t0 + j] = atan2f(ii, rr);
+              if (want_reim) { p.re[row_off + t0 + j] = rr; p.im[row_off + t0 + j] = ii; }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar);
+      tile_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace avsep

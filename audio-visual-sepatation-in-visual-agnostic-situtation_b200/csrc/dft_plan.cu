@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "dft_gemm.cuh"
+#include "dft_fold.cuh"
 #include "warp_taps.h"
 
 namespace avsep {
@@ -48,6 +49,46 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict
   const size_t o = (size_t)s * Lpad + i0;
   *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(out + lo_stride + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// Folded operand of the forward transform (dft_fold.cuh): for every frame t and n < 512
+//   E[n] = x[n] + x[1022 - n],  O[n] = x[n] - x[1022 - n]   (E[0] = x[0], E[511] = x[511], O[0] = O[511] = 0)
+// with x the reflect-padded frame, written as bf16 hi/lo planes [kind(E,O)][split][S_cap][T][512].
+__global__ void __launch_bounds__(128) wave_fold_kernel(const float* __restrict__ wave, int S, int L, int T, size_t plane_stride,
+                                                        __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
+  const int t = blockIdx.x, s = blockIdx.y;
+  const bool is_mix = mix_N > 0 && s < mix_B;
+  const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
+  const size_t src_stride = (size_t)mix_B * L;
+  auto sample = [&](int i) -> float {              // i = index into the padded signal
+    int j = i - AVSEP_N_FFT / 2;
+    if (j < 0) j = -j;
+    if (j >= L) j = 2 * (L - 1) - j;
+    if (j < 0 || j >= L) return 0.f;
+    float x = __ldg(w + j);
+    if (is_mix)
+      for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
+    return x;
+  };
+  const int n0 = threadIdx.x * 4;
+  const int base = t * AVSEP_HOP;
+  __align__(8) __nv_bfloat16 v[4][4];              // [kind * 2 + split][e]
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int n = n0 + e;
+    const float a = sample(base + n);
+    float E = a, O = 0.f;
+    if (n >= 1 && n <= AVSEP_N_FFT / 2 - 1) {
+      const float b = sample(base + AVSEP_N_FFT - n);
+      E = a + b;
+      O = a - b;
+    }
+    split_bf16(E, v[0][e], v[1][e]);
+    split_bf16(O, v[2][e], v[3][e]);
+  }
+  const size_t o = ((size_t)s * T + t) * FOLD_K + n0;
+#pragma unroll
+  for (int pl = 0; pl < 4; ++pl) *reinterpret_cast<uint2*>(out + pl * plane_stride + o) = *reinterpret_cast<const uint2*>(v[pl]);
 }
 
 // Fallback when the overlapping-row descriptor is not available: materialise frames [S, T, 1024].
@@ -220,6 +261,10 @@ struct avsep_plan {
   __nv_bfloat16* wave_split = nullptr;  // [2][S_cap][Lpad]   (overlap) or [2][S_cap][T][1024] (frames)
   __nv_bfloat16* spec_split = nullptr;  // [2][S_cap][T][1024], allocated on first inverse call
   float* inv_env = nullptr;             // [256 * (T + 3)]
+  bool fold = true;                     // forward transform through the folded (half-work) GEMM
+  __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
+  __nv_bfloat16* fold_split = nullptr;  // [4][S_cap][T][512]
+  CUtensorMap tm_basis_fold, tm_fold;
   int* err_flag = nullptr;
   CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave, tm_spec;
   bool tm_spec_valid = false;
@@ -266,6 +311,20 @@ static int build_maps(avsep_plan* pl) {
       rc = encode_map(&pl->tm_wave, pl->wave_split, 3, dims, strides, box, bk);
       if (rc) return rc;
     }
+  }
+  if (pl->basis_fold && pl->fold_split) {
+    cuuint64_t dimsA[2] = {(cuuint64_t)FOLD_K, (cuuint64_t)(4 * FOLD_BINS)};
+    cuuint64_t stridesA[1] = {(cuuint64_t)FOLD_K * 2};
+    cuuint32_t boxA[2] = {(cuuint32_t)std::min(bk, 64), (cuuint32_t)FOLD_TILE_M};
+    const int fbk = bk == 16 ? 32 : bk;                     // the folded kernel has BK = 32 / 64 variants only
+    boxA[0] = (cuuint32_t)fbk;
+    int rc = encode_map(&pl->tm_basis_fold, pl->basis_fold, 2, dimsA, stridesA, boxA, fbk);
+    if (rc) return rc;
+    cuuint64_t dimsB[3] = {(cuuint64_t)FOLD_K, (cuuint64_t)pl->T, (cuuint64_t)(4 * pl->max_signals)};
+    cuuint64_t stridesB[2] = {(cuuint64_t)FOLD_K * 2, (cuuint64_t)pl->T * FOLD_K * 2};
+    cuuint32_t boxB[3] = {(cuuint32_t)fbk, (cuuint32_t)FOLD_TILE_N, 1};
+    rc = encode_map(&pl->tm_fold, pl->fold_split, 3, dimsB, stridesB, boxB, fbk);
+    if (rc) return rc;
   }
   if (pl->spec_split) {
     cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
@@ -319,6 +378,41 @@ static void fill_basis(std::vector<uint16_t>& fwd, std::vector<uint16_t>& inv) {
   }
 }
 
+static void fill_basis_fold(std::vector<uint16_t>& out) {
+  const int NF = AVSEP_N_FFT;
+  out.assign((size_t)4 * FOLD_BINS * FOLD_K, 0);
+  for (int f = 0; f < FOLD_BINS; ++f)
+    for (int n = 0; n < FOLD_K; ++n) {
+      const double win = 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)NF);
+      const int a = (int)(((long long)f * n) % NF);
+      const double ang = 2.0 * M_PI * (double)a / (double)NF;
+      const double vals[2] = {win * std::cos(ang), -win * std::sin(ang)};
+      for (int kind = 0; kind < 2; ++kind) {
+        const float v = (float)vals[kind];
+        const uint16_t hi = host_f32_to_bf16(v);
+        const uint16_t lo = host_f32_to_bf16(v - host_bf16_to_f32(hi));
+        out[((size_t)(kind * 2 + 0) * FOLD_BINS + f) * FOLD_K + n] = hi;
+        out[((size_t)(kind * 2 + 1) * FOLD_BINS + f) * FOLD_K + n] = lo;
+      }
+    }
+}
+
+static int launch_fold(avsep_plan* pl, FoldParams prm, cudaStream_t stream) {
+  const int grid = std::min(prm.total_tiles, sm_count());
+  if (grid <= 0) return AVSEP_OK;
+  if (pl->kblock == 64) {
+    auto kern = dft_fold_fwd_kernel<64>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FoldCfg<64>::SMEM_BYTES));
+    kern<<<grid, FOLD_THREADS, FoldCfg<64>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
+  } else {
+    auto kern = dft_fold_fwd_kernel<32>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FoldCfg<32>::SMEM_BYTES));
+    kern<<<grid, FOLD_THREADS, FoldCfg<32>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
+  }
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
 template <int EPI>
 static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB, DftParams prm, cudaStream_t stream) {
   const int grid = std::min(prm.total_tiles, sm_count());
@@ -363,6 +457,14 @@ static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_
     const size_t lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
     wave_frames_kernel<<<S * pl->T, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, lo_stride, pl->wave_split, mix_B, mix_N);
   }
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+static int stage_fold(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B, int mix_N) {
+  const size_t plane = (size_t)pl->max_signals * pl->T * FOLD_K;
+  dim3 grid(pl->T, S);
+  wave_fold_kernel<<<grid, 128, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, plane, pl->fold_split, mix_B, mix_N);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
@@ -436,6 +538,17 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
   PLAN_CUDA(cudaMalloc(&pl->err_flag, sizeof(int)));
   PLAN_CUDA(cudaMemset(pl->err_flag, 0, sizeof(int)));
 
+  {
+    const char* env_fold = getenv("AVSEP_DFT_FOLD");
+    pl->fold = !(env_fold && atoi(env_fold) == 0);
+    std::vector<uint16_t> fb;
+    fill_basis_fold(fb);
+    PLAN_CUDA(cudaMalloc(&pl->basis_fold, fb.size() * 2));
+    PLAN_CUDA(cudaMemcpy(pl->basis_fold, fb.data(), fb.size() * 2, cudaMemcpyHostToDevice));
+    const size_t fold_elems = (size_t)4 * max_signals * pl->T * FOLD_K;
+    PLAN_CUDA(cudaMalloc(&pl->fold_split, fold_elems * sizeof(__nv_bfloat16)));
+    pl->workspace += fb.size() * 2 + fold_elems * sizeof(__nv_bfloat16);
+  }
   // staging buffer: large enough for either layout decision below
   {
     const size_t ov = (size_t)2 * max_signals * pl->Lpad;
@@ -468,6 +581,8 @@ int avsep_plan_destroy(avsep_plan* pl) {
   cudaFree(pl->wave_split);
   cudaFree(pl->spec_split);
   cudaFree(pl->inv_env);
+  cudaFree(pl->basis_fold);
+  cudaFree(pl->fold_split);
   cudaFree(pl->err_flag);
   delete pl;
   return AVSEP_OK;
@@ -476,6 +591,12 @@ int avsep_plan_destroy(avsep_plan* pl) {
 int avsep_plan_frames(const avsep_plan* pl) { return pl ? pl->T : 0; }
 int avsep_plan_istft_len(const avsep_plan* pl) { return pl ? pl->out_len : 0; }
 size_t avsep_plan_workspace_bytes(const avsep_plan* pl) { return pl ? pl->workspace : 0; }
+
+int avsep_plan_set_fold(avsep_plan* pl, int enable) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fold: plan is null");
+  pl->fold = enable != 0;
+  return AVSEP_OK;
+}
 
 int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_kblock: plan is null");
@@ -496,6 +617,24 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   AVSEP_REQUIRE(S >= 0 && S <= pl->max_signals, "avsep_stft: S = %d exceeds the plan capacity %d", S, pl->max_signals);
   if (S == 0) return AVSEP_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (pl->fold) {
+    int rcf = stage_fold(pl, wave_dev, S, stream, mix_B, mix_N);
+    if (rcf) return rcf;
+    FoldParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.num_signals = S;
+    fp.T = pl->T;
+    fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
+    fp.total_tiles = S * fp.n_tiles * FOLD_M_TILES;
+    fp.s_cap = pl->max_signals;
+    fp.mag = mag_dev;
+    fp.phase = phase_dev;
+    fp.re = re_dev;
+    fp.im = im_dev;
+    fp.reim_count = reim_count;
+    fp.err_flag = pl->err_flag;
+    return launch_fold(pl, fp, stream);
+  }
   int rc = stage_waves(pl, wave_dev, S, stream, mix_B, mix_N);
   if (rc) return rc;
   DftParams prm = base_params(pl, S);
@@ -595,6 +734,18 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     AVSEP_REQUIRE(pl->T <= DFT_TILE_N, "avsep_debug_gemm_only: inverse needs T <= %d", DFT_TILE_N);
     prm.wav = out_dev;
     return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, (cudaStream_t)stream_);
+  }
+  if (pl->fold) {
+    FoldParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.num_signals = S;
+    fp.T = pl->T;
+    fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
+    fp.total_tiles = S * fp.n_tiles * FOLD_M_TILES;
+    fp.s_cap = pl->max_signals;
+    fp.mag = out_dev;
+    fp.err_flag = pl->err_flag;
+    return launch_fold(pl, fp, (cudaStream_t)stream_);
   }
   prm.mag = out_dev;
   return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, (cudaStream_t)stream_);

@@ -108,6 +108,9 @@ int avsep_debug_gemm_only(avsep_plan* plan, int inverse, int S, float* out_dev, 
 int avsep_debug_basis(avsep_plan* plan, int inverse, float* out_host);
 /* staged forward operand (hi + lo) of signal s as fp32 on the host: out_host [T, 1024] */
 int avsep_debug_staged_frames(avsep_plan* plan, int s, float* out_host);
+/* enable = 1 (default): the forward transform uses the folded GEMM (real-input symmetry, half the tensor work);
+ * 0: the plain 1024 x 1024 DFT GEMM (also what the debug hooks above exercise). */
+int avsep_plan_set_fold(avsep_plan* plan, int enable);
 /* selects the K-block of the GEMM pipeline: 16 (32B swizzle, 9 stages), 32 (64B swizzle, 4 stages) or
  * 64 (128B swizzle, 2 stages) */
 int avsep_plan_set_kblock(avsep_plan* plan, int kblock);

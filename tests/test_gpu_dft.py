@@ -73,6 +73,7 @@ def test_raw_gemm_matches_staged_operands(kblock, overlap):
     finally:
         os.environ.pop("AVSEP_DFT_NO_OVERLAP_TMA", None)
     plan.set_kblock(kblock)
+    plan.set_fold(False)                  # the raw-accumulator hook exercises the plain 1024 x 1024 GEMM
     S = 3
     w = torch.from_numpy(_signals(S)).cuda()
     mag, _ = av.stft(w, plan=plan)
@@ -112,6 +113,31 @@ def test_stft_vs_oracle():
         assert np.max(np.abs(rec - spec)) / np.max(np.abs(spec)) < TOL
     err = relerr(mag[0].cpu().numpy(), O.stft_magphase(wav[0])[0])
     print(f"stft max-norm relative error {err:.3e}")
+
+
+@pytest.mark.parametrize("kblock", [64, 32])
+def test_folded_and_plain_gemm_agree(kblock):
+    """The folded (E/O symmetric) forward transform vs the plain DFT GEMM vs the oracle."""
+    S = 3
+    wav = _signals(S, seed=21)
+    w = torch.from_numpy(wav).cuda()
+    plan = av.Plan(S, L)
+    plan.set_kblock(kblock)
+    plan.set_fold(True)
+    m1, p1, r1, i1 = av.stft(w, complex_parts=True, plan=plan)
+    plan.set_fold(False)
+    m0, p0, r0, i0 = av.stft(w, complex_parts=True, plan=plan)
+    _sync()
+    scale = float(m0.max())
+    assert float((m1 - m0).abs().max()) / scale < 2e-5
+    assert float((r1 - r0).abs().max()) / scale < 2e-5 and float((i1 - i0).abs().max()) / scale < 2e-5
+    for s in range(S):
+        spec = O.stft_complex(wav[s])
+        got = r1[s].cpu().numpy().astype(np.float64) + 1j * i1[s].cpu().numpy().astype(np.float64)
+        e = np.max(np.abs(got - spec)) / np.max(np.abs(spec))
+        assert e < TOL, e
+    print(f"folded stft max-norm relative error {e:.3e}")
+    plan.close()
 
 
 def test_stft_golden_fixture(golden):
