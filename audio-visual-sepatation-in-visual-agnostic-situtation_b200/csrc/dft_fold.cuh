@@ -102,6 +102,19 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int rest = tile / FOLD_M_TILES;
         const int nt = rest % p.n_tiles;
         const int s = rest / p.n_tiles;
+        // The staged E / O planes (1 MB per signal) do not stay in L2 between the staging kernel and this one:
+        // pull the NEXT tile's operand into L2 now, a whole tile time ahead of its TMA loads.
+        const int next = tile + gridDim.x;
+        if (next < p.total_tiles) {
+          const int nrest = next / FOLD_M_TILES;
+          const int nnt = nrest % p.n_tiles, ns = nrest / p.n_tiles;
+          for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
+            const int kind = kb / Cfg::KB_HALF;
+            const int k0 = (kb % Cfg::KB_HALF) * BK;
+            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + ns);
+            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + ns);
+          }
+        }
         for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
           const int kind = kb / Cfg::KB_HALF;                 // 0: cos x E -> Re, 1: -sin x O -> Im
           const int k0 = (kb % Cfg::KB_HALF) * BK;

@@ -54,32 +54,44 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict
 // Folded operand of the forward transform (dft_fold.cuh): for every frame t and n < 512
 //   E[n] = x[n] + x[1022 - n],  O[n] = x[n] - x[1022 - n]   (E[0] = x[0], E[511] = x[511], O[0] = O[511] = 0)
 // with x the reflect-padded frame, written as bf16 hi/lo planes [kind(E,O)][split][S_cap][T][512].
-__global__ void __launch_bounds__(128) wave_fold_kernel(const float* __restrict__ wave, int S, int L, int T, size_t plane_stride,
+constexpr int FOLD_STAGE_FRAMES = 4;                       // frames per CTA of the staging kernel
+constexpr int FOLD_STAGE_SEG = AVSEP_HOP * (FOLD_STAGE_FRAMES - 1) + 1024;   // padded samples the CTA touches (1792)
+
+__global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict__ wave, int S, int L, int T, size_t plane_stride,
                                                         __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
-  const int t = blockIdx.x, s = blockIdx.y;
+  __shared__ float seg[FOLD_STAGE_SEG];
+  const int t0 = blockIdx.x * FOLD_STAGE_FRAMES, s = blockIdx.y;
   const bool is_mix = mix_N > 0 && s < mix_B;
   const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
   const size_t src_stride = (size_t)mix_B * L;
-  auto sample = [&](int i) -> float {              // i = index into the padded signal
-    int j = i - AVSEP_N_FFT / 2;
+  // 1. the reflect-padded segment covering the CTA's frames, read once (coalesced), mixture summed on the fly
+  for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
+    int j = t0 * AVSEP_HOP + i - AVSEP_N_FFT / 2;
     if (j < 0) j = -j;
     if (j >= L) j = 2 * (L - 1) - j;
-    if (j < 0 || j >= L) return 0.f;
-    float x = __ldg(w + j);
-    if (is_mix)
-      for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
-    return x;
-  };
-  const int n0 = threadIdx.x * 4;
-  const int base = t * AVSEP_HOP;
-  __align__(8) __nv_bfloat16 v[4][4];              // [kind * 2 + split][e]
+    float x = 0.f;
+    if (j >= 0 && j < L) {
+      x = __ldg(w + j);
+      if (is_mix)
+        for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
+    }
+    seg[i] = x;
+  }
+  __syncthreads();
+  // 2. one work item per thread: frame fi, 8 consecutive n  ->  four 16-byte stores (E hi, E lo, O hi, O lo)
+  const int fi = threadIdx.x >> 6;
+  const int t = t0 + fi;
+  if (t >= T) return;
+  const int n0 = (threadIdx.x & 63) * 8;
+  const float* fr = seg + fi * AVSEP_HOP;
+  __align__(16) __nv_bfloat16 v[4][8];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < 8; ++e) {
     const int n = n0 + e;
-    const float a = sample(base + n);
+    const float a = fr[n];
     float E = a, O = 0.f;
     if (n >= 1 && n <= AVSEP_N_FFT / 2 - 1) {
-      const float b = sample(base + AVSEP_N_FFT - n);
+      const float b = fr[AVSEP_N_FFT - n];
       E = a + b;
       O = a - b;
     }
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(128) wave_fold_kernel(const float* __restrict_
   }
   const size_t o = ((size_t)s * T + t) * FOLD_K + n0;
 #pragma unroll
-  for (int pl = 0; pl < 4; ++pl) *reinterpret_cast<uint2*>(out + pl * plane_stride + o) = *reinterpret_cast<const uint2*>(v[pl]);
+  for (int pl = 0; pl < 4; ++pl) *reinterpret_cast<uint4*>(out + pl * plane_stride + o) = *reinterpret_cast<const uint4*>(v[pl]);
 }
 
 // Fallback when the overlapping-row descriptor is not available: materialise frames [S, T, 1024].
@@ -463,8 +475,8 @@ static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_
 
 static int stage_fold(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B, int mix_N) {
   const size_t plane = (size_t)pl->max_signals * pl->T * FOLD_K;
-  dim3 grid(pl->T, S);
-  wave_fold_kernel<<<grid, 128, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, plane, pl->fold_split, mix_B, mix_N);
+  dim3 grid(ceil_div(pl->T, FOLD_STAGE_FRAMES), S);
+  wave_fold_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, plane, pl->fold_split, mix_B, mix_N);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
