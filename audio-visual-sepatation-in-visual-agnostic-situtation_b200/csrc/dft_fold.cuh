@@ -49,6 +49,7 @@ struct FoldParams {
   float* re;         // optional (with im), written for signals s < reim_count
   float* im;
   int reim_count;
+  int prefetch;      // L2-prefetch the next tile's operand while loading the current one
   int* err_flag;
 };
 
@@ -103,18 +104,12 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int nt = rest % p.n_tiles;
         const int s = rest / p.n_tiles;
         // The staged E / O planes (1 MB per signal) do not stay in L2 between the staging kernel and this one:
-        // pull the NEXT tile's operand into L2 now, a whole tile time ahead of its TMA loads.
+        // while loading k-block kb of this tile, pull k-block kb of the NEXT tile into L2 (a whole tile time ahead,
+        // interleaved with the demand loads so the prefetches never queue in front of them).
         const int next = tile + gridDim.x;
-        if (next < p.total_tiles) {
-          const int nrest = next / FOLD_M_TILES;
-          const int nnt = nrest % p.n_tiles, ns = nrest / p.n_tiles;
-          for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
-            const int kind = kb / Cfg::KB_HALF;
-            const int k0 = (kb % Cfg::KB_HALF) * BK;
-            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + ns);
-            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + ns);
-          }
-        }
+        const bool has_next = next < p.total_tiles;
+        const int nrest = next / FOLD_M_TILES;
+        const int nnt = nrest % p.n_tiles, ns = nrest / p.n_tiles;
         for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
           const int kind = kb / Cfg::KB_HALF;                 // 0: cos x E -> Re, 1: -sin x O -> Im
           const int k0 = (kb % Cfg::KB_HALF) * BK;
@@ -125,6 +120,10 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_2d(&tmA, full_bar(stage), st + Cfg::A_BYTES, k0, (kind * 2 + 1) * FOLD_BINS + m * FOLD_TILE_M);
           tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES, k0, nt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + s);
           tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, nt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + s);
+          if (has_next && p.prefetch) {
+            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + ns);
+            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + ns);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -200,7 +199,7 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ii[e] = __uint_as_float(vi[j + e]);
               mg[e] = sqrtf(fmaf(rr[e], rr[e], ii[e] * ii[e]));
             }
-            *reinterpret_cast<float4*>(p.mag + row_off + t0 + j) = make_float4(mg[0], mg[1], mg[2], mg[3]);
+            __stcs(reinterpret_cast<float4*>(p.mag + row_off + t0 + j), make_float4(mg[0], mg[1], mg[2], mg[3]));
             if (p.phase)
               *reinterpret_cast<float4*>(p.phase + row_off + t0 + j) =
                   make_float4(atan2f(ii[0], rr[0]), atan2f(ii[1], rr[1]), atan2f(ii[2], rr[2]), atan2f(ii[3], rr[3]));

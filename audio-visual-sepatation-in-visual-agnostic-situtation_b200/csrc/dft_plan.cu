@@ -56,10 +56,15 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict
 // with x the reflect-padded frame, written as bf16 hi/lo planes [kind(E,O)][split][S_cap][T][512].
 constexpr int FOLD_STAGE_FRAMES = 4;                       // frames per CTA of the staging kernel
 constexpr int FOLD_STAGE_SEG = AVSEP_HOP * (FOLD_STAGE_FRAMES - 1) + 1024;   // padded samples the CTA touches (1792)
+// The mirrored term x[1022 - n] is read from a REVERSED copy of the segment so that both terms are ascending,
+// 16-byte aligned float4 reads: rev[j] = seg[FOLD_STAGE_REV - 1 - j]  =>  frame fi: x[1022 - n] = rev[c_fi + n],
+// c_fi = FOLD_STAGE_REV - 1023 - 256 fi; FOLD_STAGE_REV = 1795 makes every c_fi a multiple of 4.
+constexpr int FOLD_STAGE_REV = 1795;
 
 __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict__ wave, int S, int L, int T, size_t plane_stride,
                                                         __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
-  __shared__ float seg[FOLD_STAGE_SEG];
+  __shared__ __align__(16) float seg[FOLD_STAGE_SEG];
+  __shared__ __align__(16) float rev[FOLD_STAGE_REV + 1];
   const int t0 = blockIdx.x * FOLD_STAGE_FRAMES, s = blockIdx.y;
   const bool is_mix = mix_N > 0 && s < mix_B;
   const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
         for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
     }
     seg[i] = x;
+    rev[FOLD_STAGE_REV - 1 - i] = x;
   }
   __syncthreads();
   // 2. one work item per thread: frame fi, 8 consecutive n  ->  four 16-byte stores (E hi, E lo, O hi, O lo)
@@ -83,18 +89,18 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
   const int t = t0 + fi;
   if (t >= T) return;
   const int n0 = (threadIdx.x & 63) * 8;
-  const float* fr = seg + fi * AVSEP_HOP;
+  const float4* fa = reinterpret_cast<const float4*>(seg + fi * AVSEP_HOP + n0);
+  const float4* fb = reinterpret_cast<const float4*>(rev + (FOLD_STAGE_REV - 1023 - AVSEP_HOP * fi) + n0);
+  const float4 a0 = fa[0], a1 = fa[1], b0 = fb[0], b1 = fb[1];
+  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   __align__(16) __nv_bfloat16 v[4][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int n = n0 + e;
-    const float a = fr[n];
-    float E = a, O = 0.f;
-    if (n >= 1 && n <= AVSEP_N_FFT / 2 - 1) {
-      const float b = fr[AVSEP_N_FFT - n];
-      E = a + b;
-      O = a - b;
-    }
+    const bool paired = n >= 1 && n <= AVSEP_N_FFT / 2 - 1;
+    const float E = paired ? a[e] + b[e] : a[e];
+    const float O = paired ? a[e] - b[e] : 0.f;
     split_bf16(E, v[0][e], v[1][e]);
     split_bf16(O, v[2][e], v[3][e]);
   }
@@ -274,6 +280,7 @@ struct avsep_plan {
   __nv_bfloat16* spec_split = nullptr;  // [2][S_cap][T][1024], allocated on first inverse call
   float* inv_env = nullptr;             // [256 * (T + 3)]
   bool fold = true;                     // forward transform through the folded (half-work) GEMM
+  int fold_prefetch = 1;
   __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
   __nv_bfloat16* fold_split = nullptr;  // [4][S_cap][T][512]
   CUtensorMap tm_basis_fold, tm_fold;
@@ -553,6 +560,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
   {
     const char* env_fold = getenv("AVSEP_DFT_FOLD");
     pl->fold = !(env_fold && atoi(env_fold) == 0);
+    const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
+    pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
     std::vector<uint16_t> fb;
     fill_basis_fold(fb);
     PLAN_CUDA(cudaMalloc(&pl->basis_fold, fb.size() * 2));
@@ -606,7 +615,8 @@ size_t avsep_plan_workspace_bytes(const avsep_plan* pl) { return pl ? pl->worksp
 
 int avsep_plan_set_fold(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fold: plan is null");
-  pl->fold = enable != 0;
+  pl->fold = (enable & 1) != 0;
+  pl->fold_prefetch = (enable & 2) ? 0 : 1;          // bit 1 set: folded GEMM without the L2 prefetch (A/B timing)
   return AVSEP_OK;
 }
 
@@ -644,6 +654,7 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
     fp.re = re_dev;
     fp.im = im_dev;
     fp.reim_count = reim_count;
+    fp.prefetch = pl->fold_prefetch;
     fp.err_flag = pl->err_flag;
     return launch_fold(pl, fp, stream);
   }
@@ -756,6 +767,7 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     fp.total_tiles = S * fp.n_tiles * FOLD_M_TILES;
     fp.s_cap = pl->max_signals;
     fp.mag = out_dev;
+    fp.prefetch = pl->fold_prefetch;
     fp.err_flag = pl->err_flag;
     return launch_fold(pl, fp, (cudaStream_t)stream_);
   }

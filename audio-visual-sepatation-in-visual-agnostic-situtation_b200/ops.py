@@ -82,7 +82,7 @@ class Plan:
         check(lib.avsep_plan_set_kblock(self._h, int(kblock)), "avsep_plan_set_kblock")
 
     def set_fold(self, enable: bool) -> None:
-        check(lib.avsep_plan_set_fold(self._h, int(bool(enable))), "avsep_plan_set_fold")
+        check(lib.avsep_plan_set_fold(self._h, int(enable)), "avsep_plan_set_fold")
 
     def close(self) -> None:
         if getattr(self, "_h", None):
