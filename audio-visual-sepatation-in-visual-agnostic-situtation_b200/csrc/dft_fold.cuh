@@ -5,11 +5,10 @@
 //   Im X[f] = -sum_{n=1}^{510} w[n] sin(2 pi f n / 1022) * O[n],   O[n] = x[n] - x[1022 - n]  (O[0] = O[511] = 0)
 // so the 1024 x 1024 x T contraction per signal becomes two 512 x 512 x T ones (cos rows x E, sin rows x O).
 //
-// Tile = 128 bins x 256 frames; the Re accumulator lives in TMEM columns [0, 256), the Im accumulator in
-// [256, 512) of the SAME lanes, so an epilogue thread owns (re, im) of its bin without any exchange.  Both halves of
-// TMEM are used by one tile, so the epilogue is not overlapped with the next tile's MMAs; it is spread over 8
-// warps (2 per TMEM lane group) to keep it short (~7 % of the tile time).
-//   warp 0: TMA producer | warp 1: TMEM allocator + MMA issuer | warps 2..9: epilogue
+// Tile = 128 bins x 128 frames (UMMA M = 128, N = 128).  Accumulator buffer b holds Re in TMEM columns
+// [256 b, 256 b + 128) and Im in [256 b + 128, 256 b + 256) of the SAME lanes, so an epilogue thread owns (re, im)
+// of its bin without any exchange, and the two buffers let the epilogue of tile i overlap the MMAs of tile i + 1.
+//   warp 0: TMA producer | warp 1: TMEM allocator + MMA issuer | warps 2..9: epilogue (2 per TMEM lane group)
 #pragma once
 #include <cuda.h>
 
@@ -20,7 +19,7 @@ namespace avsep {
 constexpr int FOLD_K = 512;            // folded samples per frame
 constexpr int FOLD_BINS = 512;
 constexpr int FOLD_TILE_M = 128;
-constexpr int FOLD_TILE_N = 256;
+constexpr int FOLD_TILE_N = 128;
 constexpr int FOLD_M_TILES = FOLD_BINS / FOLD_TILE_M;   // 4
 constexpr int FOLD_THREADS = 320;
 constexpr int FOLD_SMEM_LIMIT = 232448;
@@ -41,7 +40,7 @@ struct FoldCfg {
 struct FoldParams {
   int num_signals;
   int T;
-  int n_tiles;       // ceil(T / 256)
+  int n_tiles;       // ceil(T / 128)
   int total_tiles;   // S * n_tiles * 4
   int s_cap;         // signals per (kind, split) plane of the staged operand
   float* mag;        // [S, 512, T]
@@ -65,10 +64,10 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
-  const uint32_t tempty_bar = bar_base + 8u * (2 * Cfg::STAGES + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 2));
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,8 +77,10 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 256);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 256);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -135,13 +136,14 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t idesc = umma_idesc_bf16(FOLD_TILE_M, FOLD_TILE_N);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t tile_phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar, tile_phase ^ 1u, p.err_flag, 12);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 12);
         tcgen05_fence_after();
         for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
           const int kind = kb / Cfg::KB_HALF;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(kind * FOLD_TILE_N);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * FOLD_TILE_N + kind * FOLD_TILE_N);
           const bool first = (kb % Cfg::KB_HALF) == 0;
           mbar_wait(full_bar(stage), phase, p.err_flag, 13);
           tcgen05_fence_after();
@@ -160,29 +162,31 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
-        tile_phase ^= 1u;
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
       }
     }
     __syncwarp();
   } else {
     // ===================================== epilogue (8 warps) ================================
     const int q = warp & 3;                 // TMEM lane group this warp may touch
-    const int half = (warp - 2) >> 2;       // which 128 of the 256 frame columns
-    uint32_t tile_phase = 0;
+    const int half = (warp - 2) >> 2;       // which 64 of the 128 frame columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int m = tile % FOLD_M_TILES;
       const int rest = tile / FOLD_M_TILES;
       const int nt = rest % p.n_tiles;
       const int s = rest / p.n_tiles;
-      mbar_wait(tfull_bar, tile_phase, p.err_flag, 14);
+      mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 14);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * FOLD_TILE_N);
       const int f = FOLD_TILE_M * m + 32 * q + lane;
       const size_t row_off = ((size_t)s * AVSEP_N_BINS + f) * (size_t)p.T;
       const bool vec_ok = (p.T & 3) == 0;
       const bool want_reim = p.re != nullptr && s < p.reim_count;
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         const int t0 = nt * FOLD_TILE_N + c0;
         if (t0 >= p.T) break;
         uint32_t vr[32], vi[32];
@@ -221,8 +225,9 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar);
-      tile_phase ^= 1u;
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   }
 
