@@ -286,6 +286,8 @@ struct avsep_plan {
   CUtensorMap tm_basis_fold, tm_fold;
   int* err_flag = nullptr;
   CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave, tm_spec;
+  CUtensorMap tm_wave2, tm_spec2;       // same tensors, 128-frame boxes for the CTA-pair kernel
+  bool two_cta = true;                  // cta_group::2 GEMM (one 256 x 256 tile per SM pair)
   bool tm_spec_valid = false;
   size_t workspace = 0;
 };
@@ -330,6 +332,13 @@ static int build_maps(avsep_plan* pl) {
       rc = encode_map(&pl->tm_wave, pl->wave_split, 3, dims, strides, box, bk);
       if (rc) return rc;
     }
+    {
+      cuuint32_t box2[3] = {(cuuint32_t)bk, (cuuint32_t)(DFT_TILE_N / 2), 1};
+      cuuint64_t strides_ov[2] = {(cuuint64_t)AVSEP_HOP * 2, (cuuint64_t)pl->Lpad * 2};
+      cuuint64_t strides_fr[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
+      rc = encode_map(&pl->tm_wave2, pl->wave_split, 3, dims, pl->overlap_tma ? strides_ov : strides_fr, box2, bk);
+      if (rc) return rc;
+    }
   }
   if (pl->basis_fold && pl->fold_split) {
     cuuint64_t dimsA[2] = {(cuuint64_t)FOLD_K, (cuuint64_t)(4 * FOLD_BINS)};
@@ -350,6 +359,9 @@ static int build_maps(avsep_plan* pl) {
     cuuint64_t strides[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
     cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_N, 1};
     int rc = encode_map(&pl->tm_spec, pl->spec_split, 3, dims, strides, box, bk);
+    if (rc) return rc;
+    cuuint32_t box2[3] = {(cuuint32_t)bk, (cuuint32_t)(DFT_TILE_N / 2), 1};
+    rc = encode_map(&pl->tm_spec2, pl->spec_split, 3, dims, strides, box2, bk);
     if (rc) return rc;
     pl->tm_spec_valid = true;
   }
@@ -433,7 +445,24 @@ static int launch_fold(avsep_plan* pl, FoldParams prm, cudaStream_t stream) {
 }
 
 template <int EPI>
-static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB, DftParams prm, cudaStream_t stream) {
+static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB, DftParams prm, cudaStream_t stream,
+                       const CUtensorMap* tmB2 = nullptr) {
+  if (pl->two_cta && tmB2 != nullptr && pl->kblock != 16) {
+    const int pair_tiles = prm.total_tiles / 2;
+    const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+    if (grid2 <= 0) return AVSEP_OK;
+    if (pl->kblock == 64) {
+      auto kern = dft_gemm2_kernel<64, EPI>;
+      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dft2Cfg<64, EPI>::SMEM_BYTES));
+      kern<<<grid2, DFT_THREADS, Dft2Cfg<64, EPI>::SMEM_BYTES, stream>>>(tmA, *tmB2, prm);
+    } else {
+      auto kern = dft_gemm2_kernel<32, EPI>;
+      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dft2Cfg<32, EPI>::SMEM_BYTES));
+      kern<<<grid2, DFT_THREADS, Dft2Cfg<32, EPI>::SMEM_BYTES, stream>>>(tmA, *tmB2, prm);
+    }
+    AVSEP_LAUNCH_CHECK();
+    return AVSEP_OK;
+  }
   const int grid = std::min(prm.total_tiles, sm_count());
   if (grid <= 0) return AVSEP_OK;
   if (pl->kblock == 64) {
@@ -560,6 +589,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
   {
     const char* env_fold = getenv("AVSEP_DFT_FOLD");
     pl->fold = !(env_fold && atoi(env_fold) == 0);
+    const char* env_2 = getenv("AVSEP_DFT_2CTA");
+    pl->two_cta = !(env_2 && atoi(env_2) == 0);
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
     pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
     std::vector<uint16_t> fb;
@@ -620,6 +651,12 @@ int avsep_plan_set_fold(avsep_plan* pl, int enable) {
   return AVSEP_OK;
 }
 
+int avsep_plan_set_two_cta(avsep_plan* pl, int enable) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_two_cta: plan is null");
+  pl->two_cta = enable != 0;
+  return AVSEP_OK;
+}
+
 int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_kblock: plan is null");
   AVSEP_REQUIRE(kblock == 16 || kblock == 32 || kblock == 64, "avsep_plan_set_kblock: kblock must be 16, 32 or 64 (got %d)", kblock);
@@ -666,7 +703,7 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   prm.re = re_dev;
   prm.im = im_dev;
   prm.reim_count = reim_count;
-  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, stream);
+  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, stream, &pl->tm_wave2);
 }
 }  // namespace avsep
 
@@ -726,7 +763,7 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
   AVSEP_LAUNCH_CHECK();
   DftParams prm = base_params(pl, B * nsig);
   prm.wav = wav_dev;
-  return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, stream);
+  return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, stream, &pl->tm_spec2);
 }
 
 int avsep_istft(avsep_plan* pl, const float* mag_dev, const float* phase_dev, int S, float* wav_dev, void* stream) {
@@ -743,7 +780,7 @@ int avsep_debug_raw_gemm(avsep_plan* pl, int inverse, int S, float* out_dev, voi
   DftParams prm = base_params(pl, S);
   prm.raw = out_dev;
   return launch_gemm<EPI_RAW>(pl, inverse ? pl->tm_basis_inv : pl->tm_basis_fwd, inverse ? pl->tm_spec : pl->tm_wave, prm,
-                              (cudaStream_t)stream_);
+                              (cudaStream_t)stream_, inverse ? &pl->tm_spec2 : &pl->tm_wave2);
 }
 
 // product epilogues on the operands already staged in the plan (bench.py times the GEMM kernels alone with this)
@@ -756,7 +793,7 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     if (rc) return rc;
     AVSEP_REQUIRE(pl->T <= DFT_TILE_N, "avsep_debug_gemm_only: inverse needs T <= %d", DFT_TILE_N);
     prm.wav = out_dev;
-    return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, (cudaStream_t)stream_);
+    return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, (cudaStream_t)stream_, &pl->tm_spec2);
   }
   if (pl->fold) {
     FoldParams fp;
@@ -772,7 +809,7 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     return launch_fold(pl, fp, (cudaStream_t)stream_);
   }
   prm.mag = out_dev;
-  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, (cudaStream_t)stream_);
+  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, (cudaStream_t)stream_, &pl->tm_wave2);
 }
 
 int avsep_debug_basis(avsep_plan* pl, int inverse, float* out_host) {

@@ -81,6 +81,9 @@ class Plan:
     def set_kblock(self, kblock: int) -> None:
         check(lib.avsep_plan_set_kblock(self._h, int(kblock)), "avsep_plan_set_kblock")
 
+    def set_two_cta(self, enable: bool) -> None:
+        check(lib.avsep_plan_set_two_cta(self._h, int(bool(enable))), "avsep_plan_set_two_cta")
+
     def set_fold(self, enable: bool) -> None:
         check(lib.avsep_plan_set_fold(self._h, int(enable)), "avsep_plan_set_fold")
 

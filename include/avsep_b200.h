@@ -111,6 +111,9 @@ int avsep_debug_staged_frames(avsep_plan* plan, int s, float* out_host);
 /* enable = 1 (default): the forward transform uses the folded GEMM (real-input symmetry, half the tensor work);
  * 0: the plain 1024 x 1024 DFT GEMM (also what the debug hooks above exercise). */
 int avsep_plan_set_fold(avsep_plan* plan, int enable);
+/* enable = 1 (default): the plain DFT GEMM (inverse transform, and the forward one when fold is off) runs as CTA
+ * pairs (tcgen05 cta_group::2, one 256 x 256 tile per two SMs); 0: one 128 x 256 tile per CTA. */
+int avsep_plan_set_two_cta(avsep_plan* plan, int enable);
 /* selects the K-block of the GEMM pipeline: 16 (32B swizzle, 9 stages), 32 (64B swizzle, 4 stages) or
  * 64 (128B swizzle, 2 stages) */
 int avsep_plan_set_kblock(avsep_plan* plan, int kblock);

@@ -63,8 +63,9 @@ def test_basis_tables():
     plan.close()
 
 
-@pytest.mark.parametrize("kblock,overlap", [(32, True), (64, True), (16, True), (32, False)])
-def test_raw_gemm_matches_staged_operands(kblock, overlap):
+@pytest.mark.parametrize("kblock,overlap,two_cta", [(32, True, False), (64, True, False), (16, True, False), (32, False, False),
+                                                    (64, True, True), (32, True, True), (64, False, True)])
+def test_raw_gemm_matches_staged_operands(kblock, overlap, two_cta):
     """Isolates the tensor-core pipeline: raw accumulators vs (hi+lo basis) @ (hi+lo staged frames) in float64."""
     if not overlap:
         os.environ["AVSEP_DFT_NO_OVERLAP_TMA"] = "1"
@@ -74,6 +75,7 @@ def test_raw_gemm_matches_staged_operands(kblock, overlap):
         os.environ.pop("AVSEP_DFT_NO_OVERLAP_TMA", None)
     plan.set_kblock(kblock)
     plan.set_fold(False)                  # the raw-accumulator hook exercises the plain 1024 x 1024 GEMM
+    plan.set_two_cta(two_cta)             # one 128 x 256 tile per CTA, or one 256 x 256 tile per CTA pair (cta_group::2)
     S = 3
     w = torch.from_numpy(_signals(S)).cuda()
     mag, _ = av.stft(w, plan=plan)
@@ -92,7 +94,7 @@ def test_raw_gemm_matches_staged_operands(kblock, overlap):
         exp_frames = np.stack([pad[256 * t:256 * t + 1022] for t in range(T)])
         assert relerr(frames[:, :1022], exp_frames) < 2e-5
         expect = basis.astype(np.float64) @ frames.astype(np.float64).T
-        assert relerr(raw[s].cpu().numpy(), expect) < 1e-5, f"kblock={kblock} overlap={overlap} signal {s}"
+        assert relerr(raw[s].cpu().numpy(), expect) < 1e-5, f"kblock={kblock} overlap={overlap} two_cta={two_cta} signal {s}"
     plan.close()
 
 
