@@ -239,4 +239,203 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair version of the folded transform (cta_group::2): one 256-bin x 256-frame tile per pair of SMs.
+// Each CTA stages its own 128 bins of the basis and 128 of the 256 frames; the pair's MMA has M = 256, N = 256,
+// so per SM the shared-memory traffic (operand reads + TMA writes) drops from ~158 to ~106 B/clk, below the
+// 128 B/clk limit that caps the single-CTA kernels.  Re accumulates in TMEM columns [0, 256), Im in [256, 512)
+// of each CTA's own 128 lanes; with all 512 columns in use the epilogue (8 warps per CTA) is not overlapped.
+constexpr int FOLD2_TILE_N = 256;
+
+template <int BK>
+struct Fold2Cfg {
+  static_assert(BK == 32 || BK == 64, "K block is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int A_BYTES = FOLD_TILE_M * ROW_BYTES;
+  static constexpr int B_BYTES = (FOLD2_TILE_N / 2) * ROW_BYTES;     // this CTA's 128 frames
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
+  static constexpr int KB_HALF = FOLD_K / BK;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
+  static_assert((2 * STAGES + 3) * 8 <= 256, "barrier block overflow");
+};
+
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD_THREADS, 1)
+dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FoldParams p) {
+  using Cfg = Fold2Cfg<BK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int n_tiles = (p.T + FOLD2_TILE_N - 1) / FOLD2_TILE_N;
+  const int pair_tiles = p.num_signals * n_tiles * (FOLD_M_TILES / 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 512);                   // 256 epilogue threads of each CTA of the pair
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < pair_tiles; tile += npairs) {
+        const int mp = tile % (FOLD_M_TILES / 2);
+        const int rest = tile / (FOLD_M_TILES / 2);
+        const int nt = rest % n_tiles;
+        const int s = rest / n_tiles;
+        const int row0 = (2 * mp + (int)rank) * FOLD_TILE_M;
+        const int t0 = nt * FOLD2_TILE_N + (int)rank * (FOLD2_TILE_N / 2);
+        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
+          const int kind = kb / Cfg::KB_HALF;
+          const int k0 = (kb % Cfg::KB_HALF) * BK;
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 31);
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          tma2_load_2d(&tmA, lead_full, st, k0, (kind * 2 + 0) * FOLD_BINS + row0);
+          tma2_load_2d(&tmA, lead_full, st + Cfg::A_BYTES, k0, (kind * 2 + 1) * FOLD_BINS + row0);
+          tma2_load_3d(&tmB, lead_full, st + 2 * Cfg::A_BYTES, k0, t0, (kind * 2 + 0) * p.s_cap + s);
+          tma2_load_3d(&tmB, lead_full, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, t0, (kind * 2 + 1) * p.s_cap + s);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, FOLD2_TILE_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_phase = 0;
+      for (int tile = pair; tile < pair_tiles; tile += npairs) {
+        mbar_wait(tempty_bar, tile_phase ^ 1u, p.err_flag, 32);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
+          const int kind = kb / Cfg::KB_HALF;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(kind * FOLD2_TILE_N);
+          const bool first = (kb % Cfg::KB_HALF) == 0;
+          mbar_wait(full_bar(stage), phase, p.err_flag, 33);
+          tcgen05_fence_after();
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = umma_smem_desc(st, Cfg::ROW_BYTES);
+          const uint64_t a_lo = umma_smem_desc(st + Cfg::A_BYTES, Cfg::ROW_BYTES);
+          const uint64_t b_hi = umma_smem_desc(st + 2 * Cfg::A_BYTES, Cfg::ROW_BYTES);
+          const uint64_t b_lo = umma_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::ROW_BYTES);
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t adv = (uint64_t)(k16 * 2);
+            umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (first && k16 == 0) ? 0u : 1u);
+            umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          umma_commit_2sm(empty_bar(stage), 3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar, 3);
+        tile_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue (8 warps per CTA, own 128 bins) ===========
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;             // which 128 of the 256 frame columns
+    const uint32_t lead_tempty = mapa_shared(tempty_bar, 0);
+    uint32_t tile_phase = 0;
+    for (int tile = pair; tile < pair_tiles; tile += npairs) {
+      const int mp = tile % (FOLD_M_TILES / 2);
+      const int rest = tile / (FOLD_M_TILES / 2);
+      const int nt = rest % n_tiles;
+      const int s = rest / n_tiles;
+      mbar_wait(tfull_bar, tile_phase, p.err_flag, 34);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int f = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q + lane;
+      const size_t row_off = ((size_t)s * AVSEP_N_BINS + f) * (size_t)p.T;
+      const bool vec_ok = (p.T & 3) == 0;
+      const bool want_reim = p.re != nullptr && s < p.reim_count;
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        const int t0 = nt * FOLD2_TILE_N + c0;
+        if (t0 >= p.T) break;
+        uint32_t vr[32], vi[32];
+        tmem_ld_32x32b_x32(taddr + c0, vr);
+        tmem_ld_32x32b_x32(taddr + FOLD2_TILE_N + c0, vi);
+        tmem_ld_wait();
+        if (vec_ok && t0 + 32 <= p.T) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float rr[4], ii[4], mg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              rr[e] = __uint_as_float(vr[j + e]);
+              ii[e] = __uint_as_float(vi[j + e]);
+              mg[e] = sqrtf(fmaf(rr[e], rr[e], ii[e] * ii[e]));
+            }
+            __stcs(reinterpret_cast<float4*>(p.mag + row_off + t0 + j), make_float4(mg[0], mg[1], mg[2], mg[3]));
+            if (p.phase)
+              *reinterpret_cast<float4*>(p.phase + row_off + t0 + j) =
+                  make_float4(atan2f(ii[0], rr[0]), atan2f(ii[1], rr[1]), atan2f(ii[2], rr[2]), atan2f(ii[3], rr[3]));
+            if (want_reim) {
+              *reinterpret_cast<float4*>(p.re + row_off + t0 + j) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+              *reinterpret_cast<float4*>(p.im + row_off + t0 + j) = make_float4(ii[0], ii[1], ii[2], ii[3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (t0 + j < p.T) {
+              const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
+              p.mag[row_off + t0 + j] = sqrtf(fmaf(rr, rr, ii * ii));
+              if (p.phase) p.phase[row_off + t0 + j] = atan2f(ii, rr);
+              if (want_reim) { p.re[row_off + t0 + j] = rr; p.im[row_off + t0 + j] = ii; }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive_cluster(lead_tempty);
+      tile_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 }  // namespace avsep

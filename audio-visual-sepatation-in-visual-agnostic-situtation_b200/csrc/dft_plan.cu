@@ -429,6 +429,23 @@ static void fill_basis_fold(std::vector<uint16_t>& out) {
 }
 
 static int launch_fold(avsep_plan* pl, FoldParams prm, cudaStream_t stream) {
+  if (pl->two_cta) {
+    const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
+    const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
+    const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+    if (grid2 <= 0) return AVSEP_OK;
+    if (pl->kblock == 64) {
+      auto kern = dft_fold2_fwd_kernel<64>;
+      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold2Cfg<64>::SMEM_BYTES));
+      kern<<<grid2, FOLD_THREADS, Fold2Cfg<64>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
+    } else {
+      auto kern = dft_fold2_fwd_kernel<32>;
+      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold2Cfg<32>::SMEM_BYTES));
+      kern<<<grid2, FOLD_THREADS, Fold2Cfg<32>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
+    }
+    AVSEP_LAUNCH_CHECK();
+    return AVSEP_OK;
+  }
   const int grid = std::min(prm.total_tiles, sm_count());
   if (grid <= 0) return AVSEP_OK;
   if (pl->kblock == 64) {

@@ -117,14 +117,15 @@ def test_stft_vs_oracle():
     print(f"stft max-norm relative error {err:.3e}")
 
 
-@pytest.mark.parametrize("kblock", [64, 32])
-def test_folded_and_plain_gemm_agree(kblock):
+@pytest.mark.parametrize("kblock,two_cta", [(64, True), (32, True), (64, False), (32, False)])
+def test_folded_and_plain_gemm_agree(kblock, two_cta):
     """The folded (E/O symmetric) forward transform vs the plain DFT GEMM vs the oracle."""
     S = 3
     wav = _signals(S, seed=21)
     w = torch.from_numpy(wav).cuda()
     plan = av.Plan(S, L)
     plan.set_kblock(kblock)
+    plan.set_two_cta(two_cta)
     plan.set_fold(True)
     m1, p1, r1, i1 = av.stft(w, complex_parts=True, plan=plan)
     plan.set_fold(False)
