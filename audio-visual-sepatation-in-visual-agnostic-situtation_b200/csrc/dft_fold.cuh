@@ -254,11 +254,12 @@ struct Fold2Cfg {
   static constexpr int A_BYTES = FOLD_TILE_M * ROW_BYTES;
   static constexpr int B_BYTES = (FOLD2_TILE_N / 2) * ROW_BYTES;     // this CTA's 128 frames
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
+  static constexpr int XPOSE_BYTES = 8 * 32 * 33 * 4;                // one padded 32 x 32 transpose tile per epilogue warp
+  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256 - XPOSE_BYTES) / STAGE_BYTES;
   static constexpr int KB_HALF = FOLD_K / BK;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + XPOSE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
-  static_assert((2 * STAGES + 3) * 8 <= 256, "barrier block overflow");
+  static_assert(STAGES >= 2 && (2 * STAGES + 3) * 8 <= 256, "barrier block overflow");
 };
 
 template <int BK>
@@ -268,6 +269,7 @@ dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* xpose_all = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
   const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -382,10 +384,22 @@ dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(tfull_bar, tile_phase, p.err_flag, 34);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int f = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q + lane;
-      const size_t row_off = ((size_t)s * AVSEP_N_BINS + f) * (size_t)p.T;
-      const bool vec_ok = (p.T & 3) == 0;
+      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;        // first bin of this warp's 32 TMEM lanes
+      float* xt = xpose_all + (warp - 2) * (32 * 33);
       const bool want_reim = p.re != nullptr && s < p.reim_count;
+      // A lane owns one bin (row); a plain store would scatter 32 rows per instruction.  Each 32 x 32 block is
+      // transposed through a padded shared-memory tile so that every store instruction writes 128 contiguous bytes.
+      auto store_block = [&](float* __restrict__ dst, const float (&val)[32], int t0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xt[lane * 33 + j] = val[j];
+        __syncwarp();
+        const int t = t0 + lane;
+        if (t < p.T) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) __stcs(dst + ((size_t)s * AVSEP_N_BINS + f0 + r) * (size_t)p.T + t, xt[r * 33 + lane]);
+        }
+        __syncwarp();
+      };
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         const int t0 = nt * FOLD2_TILE_N + c0;
         if (t0 >= p.T) break;
@@ -393,35 +407,25 @@ dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_ld_32x32b_x32(taddr + c0, vr);
         tmem_ld_32x32b_x32(taddr + FOLD2_TILE_N + c0, vi);
         tmem_ld_wait();
-        if (vec_ok && t0 + 32 <= p.T) {
+        float val[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float rr[4], ii[4], mg[4];
+        for (int j = 0; j < 32; ++j) {
+          const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
+          val[j] = sqrtf(fmaf(rr, rr, ii * ii));
+        }
+        store_block(p.mag, val, t0);
+        if (p.phase) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              rr[e] = __uint_as_float(vr[j + e]);
-              ii[e] = __uint_as_float(vi[j + e]);
-              mg[e] = sqrtf(fmaf(rr[e], rr[e], ii[e] * ii[e]));
-            }
-            __stcs(reinterpret_cast<float4*>(p.mag + row_off + t0 + j), make_float4(mg[0], mg[1], mg[2], mg[3]));
-            if (p.phase)
-              *reinterpret_cast<float4*>(p.phase + row_off + t0 + j) =
-                  make_float4(atan2f(ii[0], rr[0]), atan2f(ii[1], rr[1]), atan2f(ii[2], rr[2]), atan2f(ii[3], rr[3]));
-            if (want_reim) {
-              *reinterpret_cast<float4*>(p.re + row_off + t0 + j) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-              *reinterpret_cast<float4*>(p.im + row_off + t0 + j) = make_float4(ii[0], ii[1], ii[2], ii[3]);
-            }
-          }
-        } else {
+          for (int j = 0; j < 32; ++j) val[j] = atan2f(__uint_as_float(vi[j]), __uint_as_float(vr[j]));
+          store_block(p.phase, val, t0);
+        }
+        if (want_reim) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (t0 + j < p.T) {
-              const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
-              p.mag[row_off + t0 + j] = sqrtf(fmaf(rr, rr, ii * ii));
-              if (p.phase) p.phase[row_off + t0 + j] = atan2f(ii, rr);
-              if (want_reim) { p.re[row_off + t0 + j] = rr; p.im[row_off + t0 + j] = ii; }
-            }
-          }
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vr[j]);
+          store_block(p.re, val, t0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vi[j]);
+          store_block(p.im, val, t0);
         }
       }
       tcgen05_fence_before();
