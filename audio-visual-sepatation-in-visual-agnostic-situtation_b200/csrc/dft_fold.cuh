@@ -43,6 +43,7 @@ struct FoldParams {
   int n_tiles;       // ceil(T / 128)
   int total_tiles;   // S * n_tiles * 4
   int s_cap;         // signals per (kind, split) plane of the staged operand
+  int sig_base;      // global index of the first signal of this launch (chunked launches reuse the staging slots)
   float* mag;        // [S, 512, T]
   float* phase;      // optional
   float* re;         // optional (with im), written for signals s < reim_count
@@ -183,9 +184,9 @@ dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * FOLD_TILE_N);
       const int f = FOLD_TILE_M * m + 32 * q + lane;
-      const size_t row_off = ((size_t)s * AVSEP_N_BINS + f) * (size_t)p.T;
+      const size_t row_off = ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f) * (size_t)p.T;
       const bool vec_ok = (p.T & 3) == 0;
-      const bool want_reim = p.re != nullptr && s < p.reim_count;
+      const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
       for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         const int t0 = nt * FOLD_TILE_N + c0;
         if (t0 >= p.T) break;
@@ -386,7 +387,7 @@ dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;        // first bin of this warp's 32 TMEM lanes
       float* xt = xpose_all + (warp - 2) * (32 * 33);
-      const bool want_reim = p.re != nullptr && s < p.reim_count;
+      const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
       // A lane owns one bin (row); a plain store would scatter 32 rows per instruction.  Each 32 x 32 block is
       // transposed through a padded shared-memory tile so that every store instruction writes 128 contiguous bytes.
       auto store_block = [&](float* __restrict__ dst, const float (&val)[32], int t0) {
@@ -396,7 +397,7 @@ dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int t = t0 + lane;
         if (t < p.T) {
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) __stcs(dst + ((size_t)s * AVSEP_N_BINS + f0 + r) * (size_t)p.T + t, xt[r * 33 + lane]);
+          for (int r = 0; r < 32; ++r) __stcs(dst + ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0 + r) * (size_t)p.T + t, xt[r * 33 + lane]);
         }
         __syncwarp();
       };

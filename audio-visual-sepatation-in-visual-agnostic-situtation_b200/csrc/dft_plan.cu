@@ -62,10 +62,12 @@ constexpr int FOLD_STAGE_SEG = AVSEP_HOP * (FOLD_STAGE_FRAMES - 1) + 1024;   // 
 constexpr int FOLD_STAGE_REV = 1795;
 
 __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict__ wave, int S, int L, int T, size_t plane_stride,
-                                                        __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
+                                                        __nv_bfloat16* __restrict__ out, int mix_B, int mix_N, int sig_base) {
   __shared__ __align__(16) float seg[FOLD_STAGE_SEG];
   __shared__ __align__(16) float rev[FOLD_STAGE_REV + 1];
-  const int t0 = blockIdx.x * FOLD_STAGE_FRAMES, s = blockIdx.y;
+  const int t0 = blockIdx.x * FOLD_STAGE_FRAMES;
+  const int s_local = blockIdx.y;                 // slot in the staging planes
+  const int s = s_local + sig_base;               // signal in the caller's batch
   const bool is_mix = mix_N > 0 && s < mix_B;
   const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
   const size_t src_stride = (size_t)mix_B * L;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
     split_bf16(E, v[0][e], v[1][e]);
     split_bf16(O, v[2][e], v[3][e]);
   }
-  const size_t o = ((size_t)s * T + t) * FOLD_K + n0;
+  const size_t o = ((size_t)s_local * T + t) * FOLD_K + n0;
 #pragma unroll
   for (int pl = 0; pl < 4; ++pl) *reinterpret_cast<uint4*>(out + pl * plane_stride + o) = *reinterpret_cast<const uint4*>(v[pl]);
 }
@@ -281,6 +283,7 @@ struct avsep_plan {
   float* inv_env = nullptr;             // [256 * (T + 3)]
   bool fold = true;                     // forward transform through the folded (half-work) GEMM
   int fold_prefetch = 1;
+  int fold_chunk = 0;                   // signals per staging + GEMM chunk of the folded path (0 = all at once)
   __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
   __nv_bfloat16* fold_split = nullptr;  // [4][S_cap][T][512]
   CUtensorMap tm_basis_fold, tm_fold;
@@ -526,10 +529,10 @@ static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_
   return AVSEP_OK;
 }
 
-static int stage_fold(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B, int mix_N) {
+static int stage_fold(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B, int mix_N, int sig_base) {
   const size_t plane = (size_t)pl->max_signals * pl->T * FOLD_K;
   dim3 grid(ceil_div(pl->T, FOLD_STAGE_FRAMES), S);
-  wave_fold_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, plane, pl->fold_split, mix_B, mix_N);
+  wave_fold_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, plane, pl->fold_split, mix_B, mix_N, sig_base);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
@@ -608,6 +611,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     pl->fold = !(env_fold && atoi(env_fold) == 0);
     const char* env_2 = getenv("AVSEP_DFT_2CTA");
     pl->two_cta = !(env_2 && atoi(env_2) == 0);
+    const char* env_ch = getenv("AVSEP_DFT_FOLD_CHUNK");
+    pl->fold_chunk = env_ch ? atoi(env_ch) : sm_count() / 2;
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
     pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
     std::vector<uint16_t> fb;
@@ -694,23 +699,34 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   if (S == 0) return AVSEP_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (pl->fold) {
-    int rcf = stage_fold(pl, wave_dev, S, stream, mix_B, mix_N);
-    if (rcf) return rcf;
-    FoldParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.num_signals = S;
-    fp.T = pl->T;
-    fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
-    fp.total_tiles = S * fp.n_tiles * FOLD_M_TILES;
-    fp.s_cap = pl->max_signals;
-    fp.mag = mag_dev;
-    fp.phase = phase_dev;
-    fp.re = re_dev;
-    fp.im = im_dev;
-    fp.reim_count = reim_count;
-    fp.prefetch = pl->fold_prefetch;
-    fp.err_flag = pl->err_flag;
-    return launch_fold(pl, fp, stream);
+    // Chunks of (SM pairs) signals = exactly two rounds of pair tiles.  The staged E / O planes of a chunk
+    // (1 MB per signal, 74 MB) are consumed by the GEMM right after they are written and the same slots are
+    // reused by the next chunk, so they live in the 126 MB L2 instead of making a round trip through HBM
+    // (the staging kernel is otherwise bound by HBM write bandwidth, ~3.1 TB/s measured).
+    const int chunk = pl->fold_chunk > 0 ? pl->fold_chunk : S;
+    for (int c0 = 0; c0 < S; c0 += chunk) {
+      const int n = std::min(chunk, S - c0);
+      int rcf = stage_fold(pl, wave_dev, n, stream, mix_B, mix_N, c0);
+      if (rcf) return rcf;
+      FoldParams fp;
+      memset(&fp, 0, sizeof(fp));
+      fp.num_signals = n;
+      fp.T = pl->T;
+      fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
+      fp.total_tiles = n * fp.n_tiles * FOLD_M_TILES;
+      fp.s_cap = pl->max_signals;
+      fp.sig_base = c0;
+      fp.mag = mag_dev;
+      fp.phase = phase_dev;
+      fp.re = re_dev;
+      fp.im = im_dev;
+      fp.reim_count = reim_count;
+      fp.prefetch = pl->fold_prefetch;
+      fp.err_flag = pl->err_flag;
+      rcf = launch_fold(pl, fp, stream);
+      if (rcf) return rcf;
+    }
+    return AVSEP_OK;
   }
   int rc = stage_waves(pl, wave_dev, S, stream, mix_B, mix_N);
   if (rc) return rc;
