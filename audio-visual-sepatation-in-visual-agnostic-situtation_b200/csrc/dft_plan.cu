@@ -72,18 +72,29 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
   const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
   const size_t src_stride = (size_t)mix_B * L;
   // 1. the reflect-padded segment covering the CTA's frames, read once (coalesced), mixture summed on the fly
-  for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
-    int j = t0 * AVSEP_HOP + i - AVSEP_N_FFT / 2;
-    if (j < 0) j = -j;
-    if (j >= L) j = 2 * (L - 1) - j;
-    float x = 0.f;
-    if (j >= 0 && j < L) {
-      x = __ldg(w + j);
+  const int j0 = t0 * AVSEP_HOP - AVSEP_N_FFT / 2;
+  if (j0 >= 0 && j0 + FOLD_STAGE_SEG <= L) {          // interior CTA (all but the first / last two of a signal): no reflection
+    for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
+      float x = __ldg(w + j0 + i);
       if (is_mix)
-        for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
+        for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j0 + i);
+      seg[i] = x;
+      rev[FOLD_STAGE_REV - 1 - i] = x;
     }
-    seg[i] = x;
-    rev[FOLD_STAGE_REV - 1 - i] = x;
+  } else {
+    for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
+      int j = j0 + i;
+      if (j < 0) j = -j;
+      if (j >= L) j = 2 * (L - 1) - j;
+      float x = 0.f;
+      if (j >= 0 && j < L) {
+        x = __ldg(w + j);
+        if (is_mix)
+          for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
+      }
+      seg[i] = x;
+      rev[FOLD_STAGE_REV - 1 - i] = x;
+    }
   }
   __syncthreads();
   // 2. one work item per thread: frame fi, 8 consecutive n  ->  four 16-byte stores (E hi, E lo, O hi, O lo)
@@ -96,15 +107,25 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
   const float4 a0 = fa[0], a1 = fa[1], b0 = fb[0], b1 = fb[1];
   const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
   const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  __align__(16) __nv_bfloat16 v[4][8];
+  __align__(16) __nv_bfloat162 v[4][4];               // [kind * 2 + split][pair of n]
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int n = n0 + e;
-    const bool paired = n >= 1 && n <= AVSEP_N_FFT / 2 - 1;
-    const float E = paired ? a[e] + b[e] : a[e];
-    const float O = paired ? a[e] - b[e] : 0.f;
-    split_bf16(E, v[0][e], v[1][e]);
-    split_bf16(O, v[2][e], v[3][e]);
+  for (int e = 0; e < 8; e += 2) {
+    float E[2], O[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int n = n0 + e + u;
+      const bool paired = n >= 1 && n <= AVSEP_N_FFT / 2 - 1;
+      E[u] = paired ? a[e + u] + b[e + u] : a[e + u];
+      O[u] = paired ? a[e + u] - b[e + u] : 0.f;
+    }
+    const __nv_bfloat162 eh = __floats2bfloat162_rn(E[0], E[1]);
+    const float2 ehf = __bfloat1622float2(eh);
+    const __nv_bfloat162 oh = __floats2bfloat162_rn(O[0], O[1]);
+    const float2 ohf = __bfloat1622float2(oh);
+    v[0][e >> 1] = eh;
+    v[1][e >> 1] = __floats2bfloat162_rn(E[0] - ehf.x, E[1] - ehf.y);
+    v[2][e >> 1] = oh;
+    v[3][e >> 1] = __floats2bfloat162_rn(O[0] - ohf.x, O[1] - ohf.y);
   }
   const size_t o = ((size_t)s_local * T + t) * FOLD_K + n0;
 #pragma unroll
@@ -158,8 +179,10 @@ struct SpecPrepParams {
   size_t lo_stride;
 };
 
+constexpr int SPEC_PITCH = 68;      // floats per time row of the transpose tile: 64 bins + 4 (keeps rows 16-byte aligned)
+
 __global__ void __launch_bounds__(256) spec_prep_kernel(const SpecPrepParams p) {
-  __shared__ float tile[2][32][65];
+  __shared__ __align__(16) float tile[2][32][SPEC_PITCH];
   const int b = blockIdx.z;
   const int f0 = blockIdx.y * 64;
   const int t0 = blockIdx.x * 32;
@@ -167,21 +190,23 @@ __global__ void __launch_bounds__(256) spec_prep_kernel(const SpecPrepParams p) 
   const int ty = threadIdx.x >> 5;
   const int t = t0 + tx;
   const bool t_ok = t < p.T;
+  // a thread owns 8 CONSECUTIVE bins of one frame: consecutive bins share un-warp rows, so the x-interpolated value
+  // of the two most recent mask rows is kept in registers (4x fewer mask loads than a 4-tap gather per element)
+  const int fb = f0 + ty * 8;
   float bre[8], bim[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int f = f0 + ty + 8 * i;
     bre[i] = 0.f;
     bim[i] = 0.f;
     if (t_ok) {
-      const size_t o = ((size_t)b * AVSEP_N_BINS + f) * p.T + t;
+      const size_t o = ((size_t)b * AVSEP_N_BINS + fb + i) * p.T + t;
       if (p.re) {
-        bre[i] = p.re[o];
-        bim[i] = p.im[o];
+        bre[i] = __ldg(p.re + o);
+        bim[i] = __ldg(p.im + o);
       } else {
-        const float mg = p.mag[o];
+        const float mg = __ldg(p.mag + o);
         float sn, cs;
-        sincosf(p.phase[o], &sn, &cs);
+        sincosf(__ldg(p.phase + o), &sn, &cs);
         bre[i] = mg * cs;
         bim[i] = mg * sn;
       }
@@ -190,56 +215,59 @@ __global__ void __launch_bounds__(256) spec_prep_kernel(const SpecPrepParams p) 
   int x0 = 0;
   float fx = 0.f;
   if (t_ok && p.log_freq) {
-    x0 = p.xtap.i0[t];
-    fx = p.xtap.frac[t];
+    x0 = __ldg(p.xtap.i0 + t);
+    fx = __ldg(p.xtap.frac + t);
   }
+  const bool xa = x0 >= 0, xb = x0 + 1 < p.T;
   const int nsig = p.N + p.include_mix;
   for (int j = 0; j < nsig; ++j) {
     const int n = j - p.include_mix;   // -1 = mixture (mask 1)
+    const float* mp = n >= 0 ? p.masks + ((size_t)n * p.B + b) * (size_t)p.Hm * p.T : nullptr;
+    int cy0 = -2, cy1 = -2;
+    float cv0 = 0.f, cv1 = 0.f;
+    auto row = [&](int y) -> float {                       // x-interpolated mask row y at this frame (0 outside)
+      if (y == cy0) return cv0;
+      if (y == cy1) return cv1;
+      if (y < 0 || y >= p.Hm) return 0.f;
+      const float* r = mp + (size_t)y * p.T;
+      return (xa ? (1.f - fx) * __ldg(r + x0) : 0.f) + (xb ? fx * __ldg(r + x0 + 1) : 0.f);
+    };
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int fl = ty + 8 * i;
       float mk = 1.f;
       if (n >= 0 && t_ok) {
-        const float* mp = p.masks + ((size_t)n * p.B + b) * (size_t)p.Hm * p.T;
         if (p.log_freq) {
-          const int f = f0 + fl;
-          const int y0 = p.ytap.i0[f];
-          const float fy = p.ytap.frac[f];
-          float r0 = 0.f, r1 = 0.f;
-          const bool xa = x0 >= 0, xb = x0 + 1 < p.T;
-          if (y0 >= 0) {
-            const float* r = mp + (size_t)y0 * p.T;
-            r0 = (xa ? (1.f - fx) * __ldg(r + x0) : 0.f) + (xb ? fx * __ldg(r + x0 + 1) : 0.f);
-          }
-          if (y0 + 1 < p.Hm) {
-            const float* r = mp + (size_t)(y0 + 1) * p.T;
-            r1 = (xa ? (1.f - fx) * __ldg(r + x0) : 0.f) + (xb ? fx * __ldg(r + x0 + 1) : 0.f);
-          }
+          const int y0 = __ldg(p.ytap.i0 + fb + i);
+          const float fy = __ldg(p.ytap.frac + fb + i);
+          const float r0 = row(y0), r1 = row(y0 + 1);
+          cy0 = y0; cv0 = r0; cy1 = y0 + 1; cv1 = r1;
           mk = (1.f - fy) * r0 + fy * r1;
         } else {
-          mk = __ldg(mp + (size_t)(f0 + fl) * p.T + t);
+          mk = __ldg(mp + (size_t)(fb + i) * p.T + t);
         }
         if (p.binary) mk = mk > p.thres ? 1.f : 0.f;
       }
-      tile[0][tx][fl] = bre[i] * mk;
-      tile[1][tx][fl] = bim[i] * mk;
+      tile[0][tx][ty * 8 + i] = bre[i] * mk;
+      tile[1][tx][ty * 8 + i] = bim[i] * mk;
     }
     __syncthreads();
-    // write 32 time rows x (64 re + 64 im) x (hi, lo): 16-byte chunks of 8 bf16
+    // write 32 time rows x (64 re + 64 im) x (hi, lo): one 128-bit shared load -> two 8-byte stores (4 bf16) per item
     const size_t sig = (size_t)b * nsig + j;
-    for (int c = threadIdx.x; c < 32 * 2 * 8; c += 256) {
-      const int tr = c >> 4;           // time row in tile
-      const int part = (c >> 3) & 1;   // 0 re, 1 im
-      const int ch = c & 7;            // chunk of 8 bins
+    for (int c = threadIdx.x; c < 32 * 2 * 16; c += 256) {
+      const int tr = c >> 5;            // time row in tile
+      const int part = (c >> 4) & 1;    // 0 re, 1 im
+      const int g = c & 15;             // group of 4 bins
       if (t0 + tr < p.T) {
-        __align__(16) __nv_bfloat16 hi[8];
-        __align__(16) __nv_bfloat16 lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(tile[part][tr][ch * 8 + e], hi[e], lo[e]);
-        const size_t o = (sig * p.T + (t0 + tr)) * DFT_K + part * AVSEP_N_BINS + f0 + ch * 8;
-        *reinterpret_cast<uint4*>(p.out + o) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(p.out + p.lo_stride + o) = *reinterpret_cast<const uint4*>(lo);
+        const float4 v = *reinterpret_cast<const float4*>(&tile[part][tr][g * 4]);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f0h = __bfloat1622float2(h0), f1h = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0h.x, v.y - f0h.y), l1 = __floats2bfloat162_rn(v.z - f1h.x, v.w - f1h.y);
+        const size_t o = (sig * p.T + (t0 + tr)) * DFT_K + part * AVSEP_N_BINS + f0 + g * 4;
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(p.out + o) = hv;
+        *reinterpret_cast<uint2*>(p.out + p.lo_stride + o) = lv;
       }
     }
     __syncthreads();
@@ -612,7 +640,7 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     const char* env_2 = getenv("AVSEP_DFT_2CTA");
     pl->two_cta = !(env_2 && atoi(env_2) == 0);
     const char* env_ch = getenv("AVSEP_DFT_FOLD_CHUNK");
-    pl->fold_chunk = env_ch ? atoi(env_ch) : sm_count() / 2;
+    pl->fold_chunk = env_ch ? atoi(env_ch) : 0;     // measured: chunking is neutral (0.584 ms/step either way), so one launch pair
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
     pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
     std::vector<uint16_t> fb;
@@ -699,10 +727,9 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   if (S == 0) return AVSEP_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (pl->fold) {
-    // Chunks of (SM pairs) signals = exactly two rounds of pair tiles.  The staged E / O planes of a chunk
-    // (1 MB per signal, 74 MB) are consumed by the GEMM right after they are written and the same slots are
-    // reused by the next chunk, so they live in the 126 MB L2 instead of making a round trip through HBM
-    // (the staging kernel is otherwise bound by HBM write bandwidth, ~3.1 TB/s measured).
+    // Optional chunking (AVSEP_DFT_FOLD_CHUNK = signals per chunk, e.g. 74 = two rounds of pair tiles): the staged
+    // E / O planes of a chunk (1 MB per signal) are then consumed by the GEMM right after they are written and
+    // the slots are reused, so they can stay in the 126 MB L2.  Measured neutral on B200, hence off by default.
     const int chunk = pl->fold_chunk > 0 ? pl->fold_chunk : S;
     for (int c0 = 0; c0 < S; c0 += chunk) {
       const int n = std::min(chunk, S - c0);
