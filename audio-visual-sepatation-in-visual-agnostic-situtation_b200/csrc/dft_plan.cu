@@ -72,29 +72,18 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
   const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
   const size_t src_stride = (size_t)mix_B * L;
   // 1. the reflect-padded segment covering the CTA's frames, read once (coalesced), mixture summed on the fly
-  const int j0 = t0 * AVSEP_HOP - AVSEP_N_FFT / 2;
-  if (j0 >= 0 && j0 + FOLD_STAGE_SEG <= L) {          // interior CTA (all but the first / last two of a signal): no reflection
-    for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
-      float x = __ldg(w + j0 + i);
+  for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
+    int j = t0 * AVSEP_HOP + i - AVSEP_N_FFT / 2;
+    if (j < 0) j = -j;
+    if (j >= L) j = 2 * (L - 1) - j;
+    float x = 0.f;
+    if (j >= 0 && j < L) {
+      x = __ldg(w + j);
       if (is_mix)
-        for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j0 + i);
-      seg[i] = x;
-      rev[FOLD_STAGE_REV - 1 - i] = x;
+        for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
     }
-  } else {
-    for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
-      int j = j0 + i;
-      if (j < 0) j = -j;
-      if (j >= L) j = 2 * (L - 1) - j;
-      float x = 0.f;
-      if (j >= 0 && j < L) {
-        x = __ldg(w + j);
-        if (is_mix)
-          for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
-      }
-      seg[i] = x;
-      rev[FOLD_STAGE_REV - 1 - i] = x;
-    }
+    seg[i] = x;
+    rev[FOLD_STAGE_REV - 1 - i] = x;
   }
   __syncthreads();
   // 2. one work item per thread: frame fi, 8 consecutive n  ->  four 16-byte stores (E hi, E lo, O hi, O lo)
@@ -107,25 +96,15 @@ __global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict_
   const float4 a0 = fa[0], a1 = fa[1], b0 = fb[0], b1 = fb[1];
   const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
   const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  __align__(16) __nv_bfloat162 v[4][4];               // [kind * 2 + split][pair of n]
+  __align__(16) __nv_bfloat16 v[4][8];
 #pragma unroll
-  for (int e = 0; e < 8; e += 2) {
-    float E[2], O[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int n = n0 + e + u;
-      const bool paired = n >= 1 && n <= AVSEP_N_FFT / 2 - 1;
-      E[u] = paired ? a[e + u] + b[e + u] : a[e + u];
-      O[u] = paired ? a[e + u] - b[e + u] : 0.f;
-    }
-    const __nv_bfloat162 eh = __floats2bfloat162_rn(E[0], E[1]);
-    const float2 ehf = __bfloat1622float2(eh);
-    const __nv_bfloat162 oh = __floats2bfloat162_rn(O[0], O[1]);
-    const float2 ohf = __bfloat1622float2(oh);
-    v[0][e >> 1] = eh;
-    v[1][e >> 1] = __floats2bfloat162_rn(E[0] - ehf.x, E[1] - ehf.y);
-    v[2][e >> 1] = oh;
-    v[3][e >> 1] = __floats2bfloat162_rn(O[0] - ohf.x, O[1] - ohf.y);
+  for (int e = 0; e < 8; ++e) {
+    const int n = n0 + e;
+    const bool paired = n >= 1 && n <= AVSEP_N_FFT / 2 - 1;
+    const float E = paired ? a[e] + b[e] : a[e];
+    const float O = paired ? a[e] - b[e] : 0.f;
+    split_bf16(E, v[0][e], v[1][e]);
+    split_bf16(O, v[2][e], v[3][e]);
   }
   const size_t o = ((size_t)s_local * T + t) * FOLD_K + n0;
 #pragma unroll
