@@ -519,6 +519,7 @@ def main():
         main_reference(args, rank, world)
         return
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the one JSON line
         from avsep_b200 import parallel
         parallel.init_from_env("nccl")
     main_ours(args, rank, world, local)
