@@ -34,6 +34,28 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so pinned host buffers allocated afterwards
+    are node-local (first touch) and H2D copies do not cross the socket interconnect.  Returns the node or None."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [start, stop) of `total` mixtures owned by `rank` (what DataParallel's scatter does along dim 0);
     the first total % world ranks get one extra mixture."""
