@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/np_oracle.py header).  Used (i) to
 cross-check the numpy oracle, and (ii) as the timed CPU arm of ``bench.py``
-(``cpu_baseline`` and ``--impl reference``).  /root/reference cannot travel to
+(``cpu_baseline`` and ``--impl reference``); ``tools/torch_gpu_baseline.py`` runs the same
+calls with the tensors on ``cuda`` to report what stock PyTorch does on the B200.  /root/reference cannot travel to
 the GPU box, so the handful of reference functions on the path are restated
 here as the *same library calls the reference makes* (``F.grid_sample``,
 ``torch.bmm``, ``torch.sigmoid``, ``F.binary_cross_entropy``); ``torch.stft`` /
@@ -37,7 +38,7 @@ def warpgrid(bs, HO, WO, warp=True):
 
 def stft_magphase(wave: torch.Tensor):
     """dataset/base.py:142-147 with torch.stft standing in for librosa.stft.  wave [S, L] -> amp, phase [S,512,T]."""
-    win = torch.hann_window(N_FFT, periodic=True, dtype=wave.dtype)
+    win = torch.hann_window(N_FFT, periodic=True, dtype=wave.dtype, device=wave.device)
     spec = torch.stft(wave, N_FFT, HOP, window=win, center=True, pad_mode="reflect", return_complex=True)
     return spec.abs(), spec.angle()
 
@@ -45,7 +46,7 @@ def stft_magphase(wave: torch.Tensor):
 def istft_reconstruction(mag: torch.Tensor, phase: torch.Tensor):
     """utils.py:101-104 with torch.istft standing in for librosa.istft.  [S,512,T] -> [S, 256*(T-1)] float64."""
     spec = mag.to(torch.complex128) * torch.exp(1j * phase.to(torch.float64))
-    win = torch.hann_window(N_FFT, periodic=True, dtype=torch.float64)
+    win = torch.hann_window(N_FFT, periodic=True, dtype=torch.float64, device=mag.device)
     wav = torch.istft(spec, N_FFT, HOP, window=win, center=True)
     return wav.clamp(-1.0, 1.0)
 
@@ -56,7 +57,7 @@ def prepare(mag_mix, mags, log_freq=True, weighted_loss=True, binary_mask=True):
     B, T = mag_mix.size(0), mag_mix.size(3)
     mags = list(mags)
     if log_freq:
-        grid_warp = torch.from_numpy(warpgrid(B, 256, T, warp=True))
+        grid_warp = torch.from_numpy(warpgrid(B, 256, T, warp=True)).to(mag_mix.device)   # main.py:62-63
         mag_mix = F.grid_sample(mag_mix, grid_warp, align_corners=False)
         for n in range(len(mags)):
             mags[n] = F.grid_sample(mags[n], grid_warp, align_corners=False)
@@ -122,7 +123,7 @@ def eval_step(waves, feat_sound, vecs, scale, bias, binary_mask=True, mask_thres
         outs = [istft_reconstruction(mag_mix[:, 0], phase_mix[:, 0])]
         for n in range(S - 1):
             p = torch.sigmoid(innerprod(vecs[:, n, :], feat_sound, scale, bias))
-            grid_unwarp = torch.from_numpy(warpgrid(B, N_FFT // 2 + 1, p.size(3), warp=False))
+            grid_unwarp = torch.from_numpy(warpgrid(B, N_FFT // 2 + 1, p.size(3), warp=False)).to(p.device)   # main.py:216-219
             lin = F.grid_sample(p, grid_unwarp, align_corners=False)
             if binary_mask:
                 lin = (lin > mask_thres).float()
