@@ -245,6 +245,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
 }
+// Same arrival without the cluster-scope release, which ptxas lowers to MEMBAR.ALL.GPU (it drains every outstanding
+// global store of the thread first: microseconds after an epilogue).  For barriers that only guard TMEM or shared
+// memory the ordering comes from tcgen05.wait::ld + tcgen05.fence::before_thread_sync, resp. fence.proxy.async,
+// executed before the arrival.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
 // TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are
 // credited to `cluster_bar`, a barrier of the LEADER CTA (shared::cluster address)
 __device__ __forceinline__ void tma2_load_2d(const void* tmap, uint32_t cluster_bar, uint32_t dst, int c0, int c1) {

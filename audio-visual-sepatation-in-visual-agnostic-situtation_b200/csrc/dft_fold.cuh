@@ -51,6 +51,9 @@ struct FoldParams {
   int reim_count;
   int prefetch;      // L2-prefetch the next tile's operand while loading the current one
   int* err_flag;
+  // dft_fold3_fwd_kernel only: the raw fp32 waveforms (the E / O operand is generated inside the kernel)
+  const float* wave; // [S, L]
+  int L;
 };
 
 // basis tensor map: rows = (kind * 2 + split) * 512 + f, cols = n (512)        kind 0 = cos, 1 = -sin
@@ -430,7 +433,372 @@ dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
       tcgen05_fence_before();
-      mbar_arrive_cluster(lead_tempty);
+      mbar_arrive_cluster_relaxed(lead_tempty);
+      tile_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ======================================================================================================
+// dft_fold3: the CTA-pair folded GEMM with the E / O operand GENERATED IN THE KERNEL from the raw waveform.
+//
+// dft_fold2 reads E[n] = x[n] + x[1022 - n], O[n] = x[n] - x[1022 - n] (bf16 hi / lo) from planes that
+// wave_fold_kernel staged in HBM: 1 MB written and read back per signal, 4x the waveform itself, because folded
+// frames no longer overlap.  Here NPW producer warps per CTA read the fp32 waveform (63 MB for 240 signals: it
+// stays in L2), fold, split and store straight into the swizzled shared-memory tile the MMA reads, so the
+// staging kernel and its 2 x 252 MB of HBM traffic disappear.
+//
+// Stage (64 KB, K block 32, SWIZZLE_64B, both kinds so one waveform load feeds E and O):
+//   [cos hi | cos lo | -sin hi | -sin lo]  4 x 8 KB, this CTA's 128 bins, by TMA from the basis
+//   [E hi   | E lo   |  O hi   |  O lo  ]  4 x 8 KB, this CTA's 128 frames, by the producer warps
+// full barrier (leader CTA): 1 expect_tx arrival (TMA bytes of both CTAs) + one arrival per producer warp of both
+// CTAs, each after fence.proxy.async so the generic-proxy stores are visible to the tensor core's async proxy.
+//   warp 0: TMA (basis) | warp 1: MMA issuer | warps 2..9: epilogue | warps 10..10+NPW-1: operand producers
+// ======================================================================================================
+struct Fold3Cfg {
+  static constexpr int BK = 32;
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int SUB_BYTES = FOLD_TILE_M * ROW_BYTES;          // 8 KB: 128 rows x 32 bf16
+  static constexpr int STAGE_BYTES = 8 * SUB_BYTES;
+  static constexpr int XPOSE_BYTES = 8 * 32 * 33 * 4;
+  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256 - XPOSE_BYTES) / STAGE_BYTES;
+  static constexpr int KSTEPS = FOLD_K / BK;                         // 16
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + XPOSE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
+  static_assert(STAGES >= 2 && (2 * STAGES + 3) * 8 <= 256, "barrier block overflow");
+};
+
+// A waveform load the compiler may neither hoist, sink nor speculate: the producers rely on the loads of one K step
+// being issued back to back (no live index registers, no spills), and on nothing consuming them before the convert.
+__device__ __forceinline__ float fold3_ldg(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// centre reflect padding of sample index j: -j for j < 0, 2 (L - 1) - j for j >= L (one reflection suffices: L >= 512)
+__device__ __forceinline__ int fold3_reflect(int j, int L) {
+  j = abs(j);
+  return max(min(j, 2 * (L - 1) - j), 0);
+}
+
+// Waveform loads of one K step of one producer warp.  Lane (sub, c) owns samples n0 = 32 ks + 2 c and n0 + 1 of the
+// frames t_even + 2 i + sub: forward terms x[n0], x[n0 + 1] and mirrored terms x[1022 - n0], x[1021 - n0].
+// Interior frames (bit i of lin_mask) use two base pointers plus compile-time offsets; the first / last two frames
+// of a clip take the reflecting index path.
+template <int ITER>
+__device__ __forceinline__ void fold3_load(const float* __restrict__ w, int L, int T, int tbase, int n0, uint32_t lin_mask,
+                                           float (&a0)[ITER], float (&a1)[ITER], float (&b0)[ITER], float (&b1)[ITER]) {
+  const int jf0 = tbase * AVSEP_HOP - AVSEP_N_FFT / 2 + n0;     // x[n0] of frame tbase in signal coordinates
+  const int jm0 = tbase * AVSEP_HOP + AVSEP_N_FFT / 2 - n0;     // x[1022 - n0]
+  const float* pf = w + jf0;                                    // only dereferenced where in range
+  const float* pm = w + jm0;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    if (lin_mask & (1u << i)) {                                 // warp-uniform, computed once per tile
+      const int d = 2 * i * AVSEP_HOP;
+      a0[i] = fold3_ldg(pf + d);
+      a1[i] = fold3_ldg(pf + d + 1);
+      b0[i] = fold3_ldg(pm + d);
+      b1[i] = fold3_ldg(pm + d - 1);
+    } else {
+      const int d = (min(tbase + 2 * i, T - 1) - tbase) * AVSEP_HOP;     // frames past T are masked by the convert
+      a0[i] = fold3_ldg(w + fold3_reflect(jf0 + d, L));
+      a1[i] = fold3_ldg(w + fold3_reflect(jf0 + d + 1, L));
+      b0[i] = fold3_ldg(w + fold3_reflect(jm0 + d, L));
+      b1[i] = fold3_ldg(w + fold3_reflect(jm0 + d - 1, L));
+    }
+  }
+}
+
+constexpr int FOLD3_THREADS = 640;      // 5 warpgroups: {TMA, MMA, 2 idle} | epilogue | epilogue | producers | producers
+constexpr int FOLD3_PW = 8;             // producer warps per CTA
+
+static_assert(4 * 48 + 8 * 112 + 8 * 104 <= (FOLD3_THREADS / 32) * 96, "setmaxnreg targets exceed the CTA's register pool");
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS)); }
+
+// SETS = K steps of waveform loads a producer warp keeps in flight (register sets of 4 * 8 floats per lane).
+// A 640-thread CTA owns 640 x 96 registers and setmaxnreg only moves registers inside that pool (an .inc the pool
+// cannot satisfy blocks forever): warpgroup 0 shrinks to 48 per thread, the two epilogue warpgroups grow to 112 and
+// the two producer warpgroups to 104  (4 x 48 + 8 x 112 + 8 x 104 = 1920 = 20 warps x 96).
+template <int SETS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD3_THREADS, 1)
+dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p) {
+  using Cfg = Fold3Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* xpose_all = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int n_tiles = (p.T + FOLD2_TILE_N - 1) / FOLD2_TILE_N;
+  const int pair_tiles = p.num_signals * n_tiles * (FOLD_M_TILES / 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + 2 * FOLD3_PW);   // TMA expect_tx arrival + every producer warp of the pair
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 512);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp < 4) {
+  // warpgroup 0 (TMA warp, MMA warp, two idle warps) hands registers to the producer warpgroup
+  setmaxnreg_dec<48>();
+  if (warp == 0) {
+    // ===================================== TMA producer: basis rows (both CTAs) ================
+    // All 32 lanes first pull the waveform segment of a tile's 128 frames (135 KB, contiguous) into L2, one tile
+    // ahead of the producer warps, so their loads never wait on DRAM.
+    auto prefetch_tile = [&](int tile) {
+      if (!(p.prefetch & 1) || tile >= pair_tiles) return;
+      const int rest = tile / (FOLD_M_TILES / 2);
+      const int nt = rest % n_tiles;
+      const int s = rest / n_tiles + p.sig_base;
+      const float* w = p.wave + (size_t)s * p.L;
+      const int t_first = nt * FOLD2_TILE_N + (int)rank * (FOLD2_TILE_N / 2);
+      const int lo = max(t_first * AVSEP_HOP - AVSEP_N_FFT / 2, 0);
+      const int hi = min((t_first + FOLD2_TILE_N / 2 - 1) * AVSEP_HOP + AVSEP_N_FFT / 2, p.L - 1);
+      const char* b = reinterpret_cast<const char*>(w + lo);
+      const char* e = reinterpret_cast<const char*>(w + hi + 1);
+      b -= reinterpret_cast<uintptr_t>(b) & 127u;
+      for (const char* q = b + lane * 128; q < e; q += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+    };
+    prefetch_tile(pair);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < pair_tiles; tile += npairs) {
+      prefetch_tile(tile + npairs);
+      if (lane == 0) {
+        const int mp = tile % (FOLD_M_TILES / 2);
+        const int row0 = (2 * mp + (int)rank) * FOLD_TILE_M;
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 41);
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * 4 * Cfg::SUB_BYTES);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma2_load_2d(&tmA, lead_full, st + j * Cfg::SUB_BYTES, ks * Cfg::BK, j * FOLD_BINS + row0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, FOLD2_TILE_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_phase = 0;
+      for (int tile = pair; tile < pair_tiles; tile += npairs) {
+        mbar_wait(tempty_bar, tile_phase ^ 1u, p.err_flag, 42);
+        tcgen05_fence_after();
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 43);
+          tcgen05_fence_after();
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int kind = 0; kind < 2; ++kind) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(kind * FOLD2_TILE_N);
+            const uint64_t a_hi = umma_smem_desc(st + (2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+            const uint64_t a_lo = umma_smem_desc(st + (2 * kind + 1) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+            const uint64_t b_hi = umma_smem_desc(st + (4 + 2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+            const uint64_t b_lo = umma_smem_desc(st + (5 + 2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+#pragma unroll
+            for (int k16 = 0; k16 < Cfg::BK / 16; ++k16) {
+              const uint64_t adv = (uint64_t)(k16 * 2);
+              umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+              umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit_2sm(empty_bar(stage), 3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar, 3);
+        tile_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  }
+  } else if (warp >= 12) {
+    // ===================================== operand producers: waveform -> E / O hi / lo tiles ==
+    constexpr int RPW = (FOLD2_TILE_N / 2) / FOLD3_PW; // 16 frames (rows) per producer warp
+    constexpr int ITER = RPW / 2;                      // a warp covers 2 rows x 32 samples per iteration
+    setmaxnreg_inc<104>();
+    const int pw = warp - 12;
+    const int sub = lane >> 4, c = lane & 15;
+    const int r0 = pw * RPW;
+    const int my_tiles = pair < pair_tiles ? (pair_tiles - pair + npairs - 1) / npairs : 0;
+    const int steps = my_tiles * Cfg::KSTEPS;          // a multiple of 16, hence of SETS
+    float a0[SETS][ITER], a1[SETS][ITER], b0[SETS][ITER], b1[SETS][ITER];
+    int tbq[SETS];                                     // first frame of the rows each set was loaded for
+    const float* w = p.wave;
+    int tbase = 0, tile_i = -1;
+    uint32_t lin_mask = 0;
+    auto issue_loads = [&](int g, float (&x0)[ITER], float (&x1)[ITER], float (&y0)[ITER], float (&y1)[ITER], int& tb) {
+      const int ks = g % Cfg::KSTEPS;                  // g = flat (tile, k step) index of this pair, issued in order
+      if (g / Cfg::KSTEPS != tile_i) {
+        tile_i = g / Cfg::KSTEPS;
+        const int tile = pair + tile_i * npairs;
+        const int rest = tile / (FOLD_M_TILES / 2);
+        const int nt = rest % n_tiles;
+        const int s = rest / n_tiles + p.sig_base;
+        w = p.wave + (size_t)s * p.L;
+        tbase = nt * FOLD2_TILE_N + (int)rank * (FOLD2_TILE_N / 2) + r0 + sub;
+        // bit i: both frames of iteration i lie in [2, (L - 512) / 256], where no sample index leaves the signal
+        lin_mask = 0;
+        const int t_even = tbase - sub;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+          const int t = t_even + 2 * i;
+          if (t >= 2 && (t + 1) * AVSEP_HOP + AVSEP_N_FFT / 2 <= p.L - 1 && t + 1 < p.T) lin_mask |= 1u << i;
+        }
+      }
+      tb = tbase;
+      if (p.prefetch & 2) {                            // timing experiment: no waveform loads at all
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) x0[i] = x1[i] = y0[i] = y1[i] = 1.f;
+        return;
+      }
+      fold3_load<ITER>(w, p.L, p.T, tbase, ks * Cfg::BK + 2 * c, lin_mask, x0, x1, y0, y1);
+    };
+    auto convert_store = [&](int g, const float (&x0)[ITER], const float (&x1)[ITER], const float (&y0)[ITER],
+                             const float (&y1)[ITER], int tb) {
+      const int ks = g % Cfg::KSTEPS;
+      const int stage = g % Cfg::STAGES;
+      const uint32_t phase = (uint32_t)(g / Cfg::STAGES) & 1u;
+      const int n0 = ks * Cfg::BK + 2 * c;
+      const bool pair0 = n0 >= 1, pair1 = n0 + 1 <= AVSEP_N_FFT / 2 - 1;
+      mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 44);
+      uint8_t* bt = smem_gen + stage * Cfg::STAGE_BYTES + 4 * Cfg::SUB_BYTES;
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {
+        const int r = r0 + 2 * i + sub;
+        // SWIZZLE_64B: the 16-byte chunk index (address bits 4..5) is XORed with address bits 7..8 = (r >> 1) & 3
+        const int off = r * Cfg::ROW_BYTES + ((4 * c) ^ ((((r0 >> 1) + i) & 3) << 4));
+        const bool ok = tb + 2 * i < p.T;              // frames past the end of a ragged clip are zero rows
+        const float u0 = ok ? x0[i] : 0.f, u1 = ok ? x1[i] : 0.f;
+        const float v0 = (ok && pair0) ? y0[i] : 0.f, v1 = (ok && pair1) ? y1[i] : 0.f;
+        const float E0 = u0 + v0, E1 = u1 + v1;
+        const float O0 = pair0 ? u0 - v0 : 0.f, O1 = pair1 ? u1 - v1 : 0.f;
+        const __nv_bfloat162 eh = __floats2bfloat162_rn(E0, E1);
+        const float2 ehf = __bfloat1622float2(eh);
+        const __nv_bfloat162 el = __floats2bfloat162_rn(E0 - ehf.x, E1 - ehf.y);
+        const __nv_bfloat162 oh = __floats2bfloat162_rn(O0, O1);
+        const float2 ohf = __bfloat1622float2(oh);
+        const __nv_bfloat162 ol = __floats2bfloat162_rn(O0 - ohf.x, O1 - ohf.y);
+        *reinterpret_cast<__nv_bfloat162*>(bt + off) = eh;
+        *reinterpret_cast<__nv_bfloat162*>(bt + Cfg::SUB_BYTES + off) = el;
+        *reinterpret_cast<__nv_bfloat162*>(bt + 2 * Cfg::SUB_BYTES + off) = oh;
+        *reinterpret_cast<__nv_bfloat162*>(bt + 3 * Cfg::SUB_BYTES + off) = ol;
+      }
+      fence_proxy_async_smem();                        // generic-proxy stores -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(full_bar(stage), 0));
+    };
+#pragma unroll
+    for (int u = 0; u < SETS; ++u)
+      if (u < steps) issue_loads(u, a0[u], a1[u], b0[u], b1[u], tbq[u]);
+    for (int g0 = 0; g0 < steps; g0 += SETS) {
+#pragma unroll
+      for (int u = 0; u < SETS; ++u) {
+        convert_store(g0 + u, a0[u], a1[u], b0[u], b1[u], tbq[u]);
+        // the refill of this set is in flight while the other set is converted and the next stage frees up
+        if (g0 + u + SETS < steps) issue_loads(g0 + u + SETS, a0[u], a1[u], b0[u], b1[u], tbq[u]);
+      }
+    }
+  } else {
+    // ===================================== epilogue (8 warps per CTA, own 128 bins) ===========
+    setmaxnreg_inc<112>();
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t lead_tempty = mapa_shared(tempty_bar, 0);
+    uint32_t tile_phase = 0;
+    for (int tile = pair; tile < pair_tiles; tile += npairs) {
+      const int mp = tile % (FOLD_M_TILES / 2);
+      const int rest = tile / (FOLD_M_TILES / 2);
+      const int nt = rest % n_tiles;
+      const int s = rest / n_tiles;
+      mbar_wait(tfull_bar, tile_phase, p.err_flag, 45);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;
+      float* xt = xpose_all + (warp - 4) * (32 * 33);
+      const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
+      auto store_block = [&](float* __restrict__ dst, const float (&val)[32], int t0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xt[lane * 33 + j] = val[j];
+        __syncwarp();
+        const int t = t0 + lane;
+        if (t < p.T) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) __stcs(dst + ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0 + r) * (size_t)p.T + t, xt[r * 33 + lane]);
+        }
+        __syncwarp();
+      };
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        const int t0 = nt * FOLD2_TILE_N + c0;
+        if (t0 >= p.T) break;
+        uint32_t vr[32], vi[32];
+        tmem_ld_32x32b_x32(taddr + c0, vr);
+        tmem_ld_32x32b_x32(taddr + FOLD2_TILE_N + c0, vi);
+        tmem_ld_wait();
+        float val[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
+          val[j] = sqrtf(fmaf(rr, rr, ii * ii));
+        }
+        store_block(p.mag, val, t0);
+        if (p.phase) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = atan2f(__uint_as_float(vi[j]), __uint_as_float(vr[j]));
+          store_block(p.phase, val, t0);
+        }
+        if (want_reim) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vr[j]);
+          store_block(p.re, val, t0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vi[j]);
+          store_block(p.im, val, t0);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive_cluster_relaxed(lead_tempty);
       tile_phase ^= 1u;
     }
   }

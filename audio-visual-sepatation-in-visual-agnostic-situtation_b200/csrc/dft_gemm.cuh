@@ -482,7 +482,7 @@ dft_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DFT_TILE_N);
       const uint32_t lead_tempty = mapa_shared(tempty_bar(acc), 0);
-      dft_epilogue_tile<EPI>(p, s, nt, m, taddr, scratch, q, lane, [&]() { mbar_arrive_cluster(lead_tempty); });
+      dft_epilogue_tile<EPI>(p, s, nt, m, taddr, scratch, q, lane, [&]() { mbar_arrive_cluster_relaxed(lead_tempty); });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

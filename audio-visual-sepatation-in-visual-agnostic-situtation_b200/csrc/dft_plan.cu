@@ -294,6 +294,11 @@ struct avsep_plan {
   __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
   __nv_bfloat16* fold_split = nullptr;  // [4][S_cap][T][512]
   CUtensorMap tm_basis_fold, tm_fold;
+  CUtensorMap tm_basis_fold32;          // the same basis with 32-column SWIZZLE_64B boxes (dft_fold3)
+  bool fused_stage = true;              // dft_fold3: E / O operand generated inside the GEMM, no staging kernel
+  int fold3_sets = 1;                   // K steps of waveform loads in flight per producer warp of dft_fold3 (1 or 2; 1 measured faster)
+  const float* last_wave = nullptr;     // arguments of the last forward transform, for avsep_debug_gemm_only
+  int last_mix_B = 0, last_mix_N = 0;
   int* err_flag = nullptr;
   CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave, tm_spec;
   CUtensorMap tm_wave2, tm_spec2;       // same tensors, 128-frame boxes for the CTA-pair kernel
@@ -357,6 +362,9 @@ static int build_maps(avsep_plan* pl) {
     const int fbk = bk == 16 ? 32 : bk;                     // the folded kernel has BK = 32 / 64 variants only
     boxA[0] = (cuuint32_t)fbk;
     int rc = encode_map(&pl->tm_basis_fold, pl->basis_fold, 2, dimsA, stridesA, boxA, fbk);
+    if (rc) return rc;
+    cuuint32_t boxA32[2] = {(cuuint32_t)Fold3Cfg::BK, (cuuint32_t)FOLD_TILE_M};
+    rc = encode_map(&pl->tm_basis_fold32, pl->basis_fold, 2, dimsA, stridesA, boxA32, Fold3Cfg::BK);
     if (rc) return rc;
     cuuint64_t dimsB[3] = {(cuuint64_t)FOLD_K, (cuuint64_t)pl->T, (cuuint64_t)(4 * pl->max_signals)};
     cuuint64_t stridesB[2] = {(cuuint64_t)FOLD_K * 2, (cuuint64_t)pl->T * FOLD_K * 2};
@@ -438,7 +446,26 @@ static void fill_basis_fold(std::vector<uint16_t>& out) {
     }
 }
 
+template <int SETS>
+static int launch_fold3(avsep_plan* pl, const FoldParams& prm, int grid2, cudaStream_t stream) {
+  auto kern = dft_fold3_fwd_kernel<SETS>;
+  AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
+  kern<<<grid2, FOLD3_THREADS, Fold3Cfg::SMEM_BYTES, stream>>>(pl->tm_basis_fold32, prm);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+// mixtures summed on the device (mix_N > 0) keep the staged path: wave_fold_kernel sums the sources while staging
+static bool use_fold3(const avsep_plan* pl, int mix_N = 0) { return pl->fold && pl->two_cta && pl->fused_stage && mix_N == 0; }
+
 static int launch_fold(avsep_plan* pl, FoldParams prm, cudaStream_t stream) {
+  if (prm.wave != nullptr) {
+    const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
+    const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
+    const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+    if (grid2 <= 0) return AVSEP_OK;
+    return pl->fold3_sets == 2 ? launch_fold3<2>(pl, prm, grid2, stream) : launch_fold3<1>(pl, prm, grid2, stream);
+  }
   if (pl->two_cta) {
     const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
     const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
@@ -620,8 +647,12 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     pl->two_cta = !(env_2 && atoi(env_2) == 0);
     const char* env_ch = getenv("AVSEP_DFT_FOLD_CHUNK");
     pl->fold_chunk = env_ch ? atoi(env_ch) : 0;     // measured: chunking is neutral (0.584 ms/step either way), so one launch pair
+    const char* env_fs = getenv("AVSEP_DFT_FUSED_STAGE");
+    pl->fused_stage = !(env_fs && atoi(env_fs) == 0);
+    const char* env_pw = getenv("AVSEP_DFT_FOLD3_SETS");
+    pl->fold3_sets = (env_pw && atoi(env_pw) == 2) ? 2 : 1;
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
-    pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
+    pl->fold_prefetch = env_pf ? atoi(env_pf) : 1;
     std::vector<uint16_t> fb;
     fill_basis_fold(fb);
     PLAN_CUDA(cudaMalloc(&pl->basis_fold, fb.size() * 2));
@@ -680,6 +711,14 @@ int avsep_plan_set_fold(avsep_plan* pl, int enable) {
   return AVSEP_OK;
 }
 
+int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int load_sets) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fused_stage: plan is null");
+  AVSEP_REQUIRE(load_sets >= 0 && load_sets <= 2, "avsep_plan_set_fused_stage: load_sets must be 0 (keep), 1 or 2 (got %d)", load_sets);
+  pl->fused_stage = enable != 0;
+  if (load_sets) pl->fold3_sets = load_sets;
+  return AVSEP_OK;
+}
+
 int avsep_plan_set_two_cta(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_two_cta: plan is null");
   pl->two_cta = enable != 0;
@@ -705,6 +744,9 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   AVSEP_REQUIRE(S >= 0 && S <= pl->max_signals, "avsep_stft: S = %d exceeds the plan capacity %d", S, pl->max_signals);
   if (S == 0) return AVSEP_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
+  pl->last_wave = wave_dev;
+  pl->last_mix_B = mix_B;
+  pl->last_mix_N = mix_N;
   if (pl->fold) {
     // Optional chunking (AVSEP_DFT_FOLD_CHUNK = signals per chunk, e.g. 74 = two rounds of pair tiles): the staged
     // E / O planes of a chunk (1 MB per signal) are then consumed by the GEMM right after they are written and
@@ -712,10 +754,13 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
     const int chunk = pl->fold_chunk > 0 ? pl->fold_chunk : S;
     for (int c0 = 0; c0 < S; c0 += chunk) {
       const int n = std::min(chunk, S - c0);
-      int rcf = stage_fold(pl, wave_dev, n, stream, mix_B, mix_N, c0);
+      const bool fused = use_fold3(pl, mix_N);
+      int rcf = fused ? AVSEP_OK : stage_fold(pl, wave_dev, n, stream, mix_B, mix_N, c0);
       if (rcf) return rcf;
       FoldParams fp;
       memset(&fp, 0, sizeof(fp));
+      fp.wave = fused ? wave_dev : nullptr;            // non-null selects dft_fold3 in launch_fold
+      fp.L = pl->wave_len;
       fp.num_signals = n;
       fp.T = pl->T;
       fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
@@ -845,6 +890,11 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     fp.mag = out_dev;
     fp.prefetch = pl->fold_prefetch;
     fp.err_flag = pl->err_flag;
+    if (use_fold3(pl, pl->last_mix_N)) {   // no staged operand exists: the kernel reads the waveform of the last avsep_stft call
+      AVSEP_REQUIRE(pl->last_wave != nullptr, "avsep_debug_gemm_only: call avsep_stft on this plan first");
+      fp.wave = pl->last_wave;
+      fp.L = pl->wave_len;
+    }
     return launch_fold(pl, fp, (cudaStream_t)stream_);
   }
   prm.mag = out_dev;

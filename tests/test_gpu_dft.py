@@ -117,15 +117,18 @@ def test_stft_vs_oracle():
     print(f"stft max-norm relative error {err:.3e}")
 
 
-@pytest.mark.parametrize("kblock,two_cta", [(64, True), (32, True), (64, False), (32, False)])
-def test_folded_and_plain_gemm_agree(kblock, two_cta):
-    """The folded (E/O symmetric) forward transform vs the plain DFT GEMM vs the oracle."""
+@pytest.mark.parametrize("kblock,two_cta,fused", [(64, True, 0), (32, True, 0), (64, False, 0), (32, False, 0),
+                                                   (64, True, 1), (64, True, 2)])
+def test_folded_and_plain_gemm_agree(kblock, two_cta, fused):
+    """The folded (E/O symmetric) forward transform vs the plain DFT GEMM vs the oracle.  fused = 0: operand staged
+    by wave_fold_kernel and read by TMA; 1 / 2: generated inside the GEMM (dft_fold3) with that many K steps of loads in flight."""
     S = 3
     wav = _signals(S, seed=21)
     w = torch.from_numpy(wav).cuda()
     plan = av.Plan(S, L)
     plan.set_kblock(kblock)
     plan.set_two_cta(two_cta)
+    plan.set_fused_stage(fused != 0, fused)
     plan.set_fold(True)
     m1, p1, r1, i1 = av.stft(w, complex_parts=True, plan=plan)
     plan.set_fold(False)
@@ -140,6 +143,26 @@ def test_folded_and_plain_gemm_agree(kblock, two_cta):
         e = np.max(np.abs(got - spec)) / np.max(np.abs(spec))
         assert e < TOL, e
     print(f"folded stft max-norm relative error {e:.3e}")
+    plan.close()
+
+
+@pytest.mark.parametrize("warps", [1, 2])
+@pytest.mark.parametrize("length", [L, 512, 3000, 70001])
+def test_fused_stage_equals_staged_operand(warps, length):
+    """dft_fold3 folds and splits the waveform in its producer warps; the values it feeds the tensor core are the
+    same bf16 pairs wave_fold_kernel stages, accumulated in the same order, so the spectra must be identical --
+    including the reflect-padded edge frames, clips shorter than one tile and clips spanning two tiles."""
+    S = 5
+    wav = _signals(S, seed=33, length=length)
+    w = torch.from_numpy(wav).cuda()
+    plan = av.Plan(S, length)
+    plan.set_fused_stage(False)
+    m0, p0, r0, i0 = av.stft(w, complex_parts=True, plan=plan)
+    plan.set_fused_stage(True, warps)
+    m1, p1, r1, i1 = av.stft(w, complex_parts=True, plan=plan)
+    _sync()
+    assert torch.equal(r0, r1) and torch.equal(i0, i1)
+    assert torch.equal(m0, m1) and torch.equal(p0, p1)
     plan.close()
 
 

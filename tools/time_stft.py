@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Time avsep_stft alone (240 signals of 65535 samples) under the current AVSEP_DFT_* environment."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import avsep_b200 as av  # noqa: E402
+
+S, L = int(os.environ.get("S", 240)), 65535
+w = torch.randn(S, L, device="cuda") * 0.1
+plan = av.Plan(S, L)
+mag = torch.empty(S, 512, 256, device="cuda")
+lib, chk = av._lib.lib, av._lib.check
+st = torch.cuda.current_stream().cuda_stream
+call = lambda: chk(lib.avsep_stft(plan._h, w.data_ptr(), S, mag.data_ptr(), None, None, None, st))
+for _ in range(5):
+    call()
+torch.cuda.synchronize()
+best = 1e9
+for rep in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 10)
+print({k: v for k, v in os.environ.items() if k.startswith("AVSEP_")}, "stft ms %.4f" % best)
