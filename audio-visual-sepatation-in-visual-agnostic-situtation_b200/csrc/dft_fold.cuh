@@ -527,11 +527,14 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS)); }
 
-// SETS = K steps of waveform loads a producer warp keeps in flight (register sets of 4 * 8 floats per lane).
+// NG = producer groups.  NG = 1: all 8 producer warps work on every K step (16 frames each).  NG = 2: warps 0..3
+// convert the even K steps and warps 4..7 the odd ones (32 frames each), so a group has two MMA step times for
+// "loads in flight -> convert -> store".  (More loads in flight per THREAD do not help: the fence.proxy.async that
+// publishes a stage also waits for the thread's outstanding global loads -- measured.)
 // A 640-thread CTA owns 640 x 96 registers and setmaxnreg only moves registers inside that pool (an .inc the pool
 // cannot satisfy blocks forever): warpgroup 0 shrinks to 48 per thread, the two epilogue warpgroups grow to 112 and
 // the two producer warpgroups to 104  (4 x 48 + 8 x 112 + 8 x 104 = 1920 = 20 warps x 96).
-template <int SETS>
+template <int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD3_THREADS, 1)
 dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p) {
   using Cfg = Fold3Cfg;
@@ -557,7 +560,7 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + 2 * FOLD3_PW);   // TMA expect_tx arrival + every producer warp of the pair
+      mbar_init(full_bar(s), 1 + 2 * (FOLD3_PW / NG));   // TMA expect_tx arrival + the producer warps of the step's group, both CTAs
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
@@ -655,21 +658,22 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
   }
   } else if (warp >= 12) {
     // ===================================== operand producers: waveform -> E / O hi / lo tiles ==
-    constexpr int RPW = (FOLD2_TILE_N / 2) / FOLD3_PW; // 16 frames (rows) per producer warp
+    constexpr int WPG = FOLD3_PW / NG;                 // warps per group
+    constexpr int RPW = (FOLD2_TILE_N / 2) / WPG;      // frames (rows) per producer warp: 16 or 32
     constexpr int ITER = RPW / 2;                      // a warp covers 2 rows x 32 samples per iteration
     setmaxnreg_inc<104>();
-    const int pw = warp - 12;
+    const int grp = (warp - 12) / WPG;
+    const int pw = (warp - 12) % WPG;
     const int sub = lane >> 4, c = lane & 15;
     const int r0 = pw * RPW;
     const int my_tiles = pair < pair_tiles ? (pair_tiles - pair + npairs - 1) / npairs : 0;
-    const int steps = my_tiles * Cfg::KSTEPS;          // a multiple of 16, hence of SETS
-    float a0[SETS][ITER], a1[SETS][ITER], b0[SETS][ITER], b1[SETS][ITER];
-    int tbq[SETS];                                     // first frame of the rows each set was loaded for
+    const int steps = my_tiles * Cfg::KSTEPS;
+    float a0[ITER], a1[ITER], b0[ITER], b1[ITER];
     const float* w = p.wave;
     int tbase = 0, tile_i = -1;
     uint32_t lin_mask = 0;
     auto issue_loads = [&](int g, float (&x0)[ITER], float (&x1)[ITER], float (&y0)[ITER], float (&y1)[ITER], int& tb) {
-      const int ks = g % Cfg::KSTEPS;                  // g = flat (tile, k step) index of this pair, issued in order
+      const int ks = g % Cfg::KSTEPS;                  // g = flat (tile, k step) index of this pair, increasing
       if (g / Cfg::KSTEPS != tile_i) {
         tile_i = g / Cfg::KSTEPS;
         const int tile = pair + tile_i * npairs;
@@ -693,27 +697,31 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
         for (int i = 0; i < ITER; ++i) x0[i] = x1[i] = y0[i] = y1[i] = 1.f;
         return;
       }
+      if (p.prefetch & 4) {                            // timing experiment: loads issued, results never consumed
+        float d0[ITER], d1[ITER], d2[ITER], d3[ITER];
+        fold3_load<ITER>(w, p.L, p.T, tbase, ks * Cfg::BK + 2 * c, lin_mask, d0, d1, d2, d3);
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) x0[i] = x1[i] = y0[i] = y1[i] = 1.f;
+        return;
+      }
       fold3_load<ITER>(w, p.L, p.T, tbase, ks * Cfg::BK + 2 * c, lin_mask, x0, x1, y0, y1);
     };
+    // fold + split the loaded samples of step g and write the bf16 pairs into the step's stage
     auto convert_store = [&](int g, const float (&x0)[ITER], const float (&x1)[ITER], const float (&y0)[ITER],
                              const float (&y1)[ITER], int tb) {
-      const int ks = g % Cfg::KSTEPS;
       const int stage = g % Cfg::STAGES;
       const uint32_t phase = (uint32_t)(g / Cfg::STAGES) & 1u;
-      const int n0 = ks * Cfg::BK + 2 * c;
+      const int n0 = (g % Cfg::KSTEPS) * Cfg::BK + 2 * c;
       const bool pair0 = n0 >= 1, pair1 = n0 + 1 <= AVSEP_N_FFT / 2 - 1;
-      mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 44);
+      mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 44);   // the MMAs that read the stage's previous contents are done
       uint8_t* bt = smem_gen + stage * Cfg::STAGE_BYTES + 4 * Cfg::SUB_BYTES;
-#pragma unroll
-      for (int i = 0; i < ITER; ++i) {
+      // Fast path (14 of 16 K steps of a full tile): every frame exists and every sample has its mirror partner, so
+      // no masking.  The generic path handles K step 0 (n = 0 has no partner), K step 15 (n = 511) and ragged tiles.
+      const bool plain = (n0 - 2 * c) != 0 && (n0 - 2 * c) != (Cfg::KSTEPS - 1) * Cfg::BK && tb - sub + RPW <= p.T;
+      auto emit = [&](int i, float E0, float E1, float O0, float O1) {
         const int r = r0 + 2 * i + sub;
         // SWIZZLE_64B: the 16-byte chunk index (address bits 4..5) is XORed with address bits 7..8 = (r >> 1) & 3
         const int off = r * Cfg::ROW_BYTES + ((4 * c) ^ ((((r0 >> 1) + i) & 3) << 4));
-        const bool ok = tb + 2 * i < p.T;              // frames past the end of a ragged clip are zero rows
-        const float u0 = ok ? x0[i] : 0.f, u1 = ok ? x1[i] : 0.f;
-        const float v0 = (ok && pair0) ? y0[i] : 0.f, v1 = (ok && pair1) ? y1[i] : 0.f;
-        const float E0 = u0 + v0, E1 = u1 + v1;
-        const float O0 = pair0 ? u0 - v0 : 0.f, O1 = pair1 ? u1 - v1 : 0.f;
         const __nv_bfloat162 eh = __floats2bfloat162_rn(E0, E1);
         const float2 ehf = __bfloat1622float2(eh);
         const __nv_bfloat162 el = __floats2bfloat162_rn(E0 - ehf.x, E1 - ehf.y);
@@ -724,21 +732,29 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
         *reinterpret_cast<__nv_bfloat162*>(bt + Cfg::SUB_BYTES + off) = el;
         *reinterpret_cast<__nv_bfloat162*>(bt + 2 * Cfg::SUB_BYTES + off) = oh;
         *reinterpret_cast<__nv_bfloat162*>(bt + 3 * Cfg::SUB_BYTES + off) = ol;
+      };
+      if (plain) {
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) emit(i, x0[i] + y0[i], x1[i] + y1[i], x0[i] - y0[i], x1[i] - y1[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+          const bool ok = tb + 2 * i < p.T;            // frames past the end of a ragged clip are zero rows
+          const float u0 = ok ? x0[i] : 0.f, u1 = ok ? x1[i] : 0.f;
+          const float v0 = (ok && pair0) ? y0[i] : 0.f, v1 = (ok && pair1) ? y1[i] : 0.f;
+          emit(i, u0 + v0, u1 + v1, pair0 ? u0 - v0 : 0.f, pair1 ? u1 - v1 : 0.f);
+        }
       }
       fence_proxy_async_smem();                        // generic-proxy stores -> visible to the MMA's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(full_bar(stage), 0));
     };
-#pragma unroll
-    for (int u = 0; u < SETS; ++u)
-      if (u < steps) issue_loads(u, a0[u], a1[u], b0[u], b1[u], tbq[u]);
-    for (int g0 = 0; g0 < steps; g0 += SETS) {
-#pragma unroll
-      for (int u = 0; u < SETS; ++u) {
-        convert_store(g0 + u, a0[u], a1[u], b0[u], b1[u], tbq[u]);
-        // the refill of this set is in flight while the other set is converted and the next stage frees up
-        if (g0 + u + SETS < steps) issue_loads(g0 + u + SETS, a0[u], a1[u], b0[u], b1[u], tbq[u]);
-      }
+    int tb = 0;
+    if (grp < steps) issue_loads(grp, a0, a1, b0, b1, tb);
+    for (int g = grp; g < steps; g += NG) {
+      convert_store(g, a0, a1, b0, b1, tb);
+      // refill AFTER the store: its fence.proxy.async would otherwise wait for these loads
+      if (g + NG < steps) issue_loads(g + NG, a0, a1, b0, b1, tb);
     }
   } else {
     // ===================================== epilogue (8 warps per CTA, own 128 bins) ===========

@@ -296,7 +296,7 @@ struct avsep_plan {
   CUtensorMap tm_basis_fold, tm_fold;
   CUtensorMap tm_basis_fold32;          // the same basis with 32-column SWIZZLE_64B boxes (dft_fold3)
   bool fused_stage = true;              // dft_fold3: E / O operand generated inside the GEMM, no staging kernel
-  int fold3_sets = 1;                   // K steps of waveform loads in flight per producer warp of dft_fold3 (1 or 2; 1 measured faster)
+  int fold3_sets = 2;                   // producer groups of dft_fold3 (1: all warps on every K step, 2: alternate K steps)
   const float* last_wave = nullptr;     // arguments of the last forward transform, for avsep_debug_gemm_only
   int last_mix_B = 0, last_mix_N = 0;
   int* err_flag = nullptr;
@@ -446,9 +446,9 @@ static void fill_basis_fold(std::vector<uint16_t>& out) {
     }
 }
 
-template <int SETS>
+template <int NG>
 static int launch_fold3(avsep_plan* pl, const FoldParams& prm, int grid2, cudaStream_t stream) {
-  auto kern = dft_fold3_fwd_kernel<SETS>;
+  auto kern = dft_fold3_fwd_kernel<NG>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
   kern<<<grid2, FOLD3_THREADS, Fold3Cfg::SMEM_BYTES, stream>>>(pl->tm_basis_fold32, prm);
   AVSEP_LAUNCH_CHECK();
@@ -649,8 +649,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     pl->fold_chunk = env_ch ? atoi(env_ch) : 0;     // measured: chunking is neutral (0.584 ms/step either way), so one launch pair
     const char* env_fs = getenv("AVSEP_DFT_FUSED_STAGE");
     pl->fused_stage = !(env_fs && atoi(env_fs) == 0);
-    const char* env_pw = getenv("AVSEP_DFT_FOLD3_SETS");
-    pl->fold3_sets = (env_pw && atoi(env_pw) == 2) ? 2 : 1;
+    const char* env_pw = getenv("AVSEP_DFT_FOLD3_GROUPS");
+    pl->fold3_sets = (env_pw && atoi(env_pw) == 1) ? 1 : 2;
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
     pl->fold_prefetch = env_pf ? atoi(env_pf) : 1;
     std::vector<uint16_t> fb;
@@ -711,11 +711,11 @@ int avsep_plan_set_fold(avsep_plan* pl, int enable) {
   return AVSEP_OK;
 }
 
-int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int load_sets) {
+int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int groups) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fused_stage: plan is null");
-  AVSEP_REQUIRE(load_sets >= 0 && load_sets <= 2, "avsep_plan_set_fused_stage: load_sets must be 0 (keep), 1 or 2 (got %d)", load_sets);
+  AVSEP_REQUIRE(groups >= 0 && groups <= 2, "avsep_plan_set_fused_stage: groups must be 0 (keep), 1 or 2 (got %d)", groups);
   pl->fused_stage = enable != 0;
-  if (load_sets) pl->fold3_sets = load_sets;
+  if (groups) pl->fold3_sets = groups;
   return AVSEP_OK;
 }
 

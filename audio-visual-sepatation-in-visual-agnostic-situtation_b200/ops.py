@@ -81,8 +81,8 @@ class Plan:
     def set_kblock(self, kblock: int) -> None:
         check(lib.avsep_plan_set_kblock(self._h, int(kblock)), "avsep_plan_set_kblock")
 
-    def set_fused_stage(self, enable: bool, load_sets: int = 0) -> None:
-        check(lib.avsep_plan_set_fused_stage(self._h, int(bool(enable)), int(load_sets)), "avsep_plan_set_fused_stage")
+    def set_fused_stage(self, enable: bool, groups: int = 0) -> None:
+        check(lib.avsep_plan_set_fused_stage(self._h, int(bool(enable)), int(groups)), "avsep_plan_set_fused_stage")
 
     def set_two_cta(self, enable: bool) -> None:
         check(lib.avsep_plan_set_two_cta(self._h, int(bool(enable))), "avsep_plan_set_two_cta")

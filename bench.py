@@ -488,7 +488,7 @@ def main_ours(args, rank, world, local):
                                   "C2 MUSIC N=2 train step: STFT(3 signals)+prepare+synth K=32+sigmoid+weighted BCE+backward"),
                         batch_per_gpu=B, global_batch=B * world, num_mix=N, K=K, samples=L, stft="1022/256", grid="256x256",
                         parallelism=f"batch-sharded x{world}, no data-path collective", numa_node_rank0=numa_node,
-                        launch=("plain launches" if args.no_graph or eval_mode else "CUDA graph replay of the 6-kernel step"),
+                        launch=("plain launches" if args.no_graph or eval_mode else "CUDA graph replay of the step's kernels (see gpu_launches / steps)"),
                         l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                      pipeline_depth=pipe_depth, timer="host wall clock around the K steps, synchronised on both sides",

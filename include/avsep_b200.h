@@ -115,11 +115,12 @@ int avsep_plan_set_fold(avsep_plan* plan, int enable);
  * pairs (tcgen05 cta_group::2, one 256 x 256 tile per two SMs); 0: one 128 x 256 tile per CTA. */
 int avsep_plan_set_two_cta(avsep_plan* plan, int enable);
 /* enable = 1 (default, needs fold and two_cta): the folded GEMM builds its E / O operand inside the kernel from the
- * fp32 waveform (producer warps writing the swizzled shared-memory tiles), so no staging kernel runs and no staged
- * planes cross HBM; 0: wave_fold_kernel stages the planes and dft_fold2 reads them by TMA (also used whenever the
- * mixture is summed on the device).  load_sets: K steps of waveform loads each producer warp keeps in flight, 1 or 2
- * (default 1, measured faster on B200); 0 keeps the setting. */
-int avsep_plan_set_fused_stage(avsep_plan* plan, int enable, int load_sets);
+ * fp32 waveform (8 producer warps per CTA fold, split to bf16 hi / lo and write the swizzled shared-memory tiles the
+ * tensor core reads), so no staging kernel runs and no staged planes cross HBM; 0: wave_fold_kernel stages the planes
+ * and dft_fold2 reads them by TMA (also what runs whenever the mixture is summed on the device).
+ * groups: 1 = all producer warps work on every K step, 2 = two groups alternate K steps (default, measured
+ * slightly faster on B200), 0 keeps the setting. */
+int avsep_plan_set_fused_stage(avsep_plan* plan, int enable, int groups);
 /* selects the K-block of the GEMM pipeline: 16 (32B swizzle, 9 stages), 32 (64B swizzle, 4 stages) or
  * 64 (128B swizzle, 2 stages) */
 int avsep_plan_set_kblock(avsep_plan* plan, int kblock);

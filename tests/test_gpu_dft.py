@@ -121,7 +121,7 @@ def test_stft_vs_oracle():
                                                    (64, True, 1), (64, True, 2)])
 def test_folded_and_plain_gemm_agree(kblock, two_cta, fused):
     """The folded (E/O symmetric) forward transform vs the plain DFT GEMM vs the oracle.  fused = 0: operand staged
-    by wave_fold_kernel and read by TMA; 1 / 2: generated inside the GEMM (dft_fold3) with that many K steps of loads in flight."""
+    by wave_fold_kernel and read by TMA; 1 / 2: generated inside the GEMM (dft_fold3) by one / two producer groups."""
     S = 3
     wav = _signals(S, seed=21)
     w = torch.from_numpy(wav).cuda()

@@ -94,7 +94,7 @@ def test_train_step_vs_oracle():
             dfeat_g.zero_()
             st.train_dev(tw, tv, tfeat, tsc, tb, dfeat_g, None, None, None, loss_g)
         side.synchronize()
-        assert av.launch_count() - before == 4 * 5                 # wave_split, dft_gemm, prepare, synth_train, finalize per step
+        assert av.launch_count() - before == 4 * 4                 # dft_fold3 (staging fused in), prepare, synth_train, finalize per step
         assert float(loss_g) == float(loss) and torch.equal(dfeat_g, dfeat)
         st.set_graph(False)
     torch.cuda.current_stream().wait_stream(side)

@@ -6,7 +6,7 @@ timeout 600 python -m pytest tests/test_gpu_dft.py -x -q -k "fused_stage or fold
 for cfg in ${FOLD3_CFGS:-"1 4 1" "1 8 1" "1 4 0" "0 4 1"}; do
   set -- $cfg
   echo "== bench fused=$1 warps=$2 prefetch=$3 =="
-  AVSEP_DFT_FUSED_STAGE=$1 AVSEP_DFT_FOLD3_WARPS=$2 AVSEP_DFT_FOLD_PREFETCH=$3 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_f$1_w$2_p$3.json 2> gpurun_out/bench_f$1_w$2_p$3.err; echo "rc=$?"
+  AVSEP_DFT_FUSED_STAGE=$1 AVSEP_DFT_FOLD3_GROUPS=$2 AVSEP_DFT_FOLD_PREFETCH=$3 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_f$1_w$2_p$3.json 2> gpurun_out/bench_f$1_w$2_p$3.err; echo "rc=$?"
   python - <<PY
 import json
 try:
