@@ -20,9 +20,11 @@ from . import hotpath
 from .hotpath import (Step, _mix_n_and_stft, _stft, assemble_windows, calc_metrics, clip_windows, istft_reconstruction, prepare,
                       separate_long_clip, stft_batch, warp, warpgrid)
 from . import parallel
+from . import bss_metrics
+from .bss_metrics import bss_eval_batch
 
 __all__ = [
-    "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel",
+    "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel", "bss_metrics", "bss_eval_batch",
     "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
     "stft", "istft", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
     "_stft", "_mix_n_and_stft", "stft_batch", "Step", "clip_windows", "assemble_windows", "separate_long_clip",

@@ -182,6 +182,13 @@ def test_calc_metrics_dropin_matches_reference_golden(golden):
     assert np.max(np.abs(np.asarray(res[5]) - g["sir"])) < 0.01
     assert np.max(np.abs(np.asarray(res[6]) - g["si_sdr"])) < 0.01
     assert abs(res[1] - float(g["sdr_avg"])) < 0.01 and abs(res[3] - float(g["sar_avg"])) < 0.01
+    # the batched device evaluator (bss_metrics.bss_eval_batch) on the same clips: no host loop, same numbers
+    res_gpu = av.calc_metrics(batch, dict(pred_masks=pm), args, get_metrics="gpu")
+    assert np.max(np.abs(np.asarray(res_gpu[4]) - g["sdr"])) < 0.01
+    assert np.max(np.abs(np.asarray(res_gpu[5]) - g["sir"])) < 0.01
+    assert np.max(np.abs(np.asarray(res_gpu[6]) - g["si_sdr"])) < 0.01
+    assert abs(res_gpu[1] - res[1]) < 1e-3 and abs(res_gpu[2] - res[2]) < 1e-3 and abs(res_gpu[3] - res[3]) < 1e-3
+    assert abs(res_gpu[7] - res[7]) < 1e-3
 
 
 def test_n3_and_batch_shapes():
