@@ -13,7 +13,7 @@ CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${R}.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-for K in dft_fold2_fwd_kernel wave_fold_kernel synth_train_kernel prepare_vec_kernel; do
+for K in dft_fold3_fwd_kernel synth_train_kernel prepare_vec_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o gpurun_out/prof_${R}_$K $CMD > gpurun_out/ncu_$K.log 2>&1
   echo "ncu $K rc=$?"
 done
