@@ -585,7 +585,7 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
     // All 32 lanes first pull the waveform segment of a tile's 128 frames (135 KB, contiguous) into L2, one tile
     // ahead of the producer warps, so their loads never wait on DRAM.
     auto prefetch_tile = [&](int tile) {
-      if (!(p.prefetch & 1) || tile >= pair_tiles) return;
+      if (!p.prefetch || tile >= pair_tiles) return;
       const int rest = tile / (FOLD_M_TILES / 2);
       const int nt = rest % n_tiles;
       const int s = rest / n_tiles + p.sig_base;
@@ -692,18 +692,6 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
         }
       }
       tb = tbase;
-      if (p.prefetch & 2) {                            // timing experiment: no waveform loads at all
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) x0[i] = x1[i] = y0[i] = y1[i] = 1.f;
-        return;
-      }
-      if (p.prefetch & 4) {                            // timing experiment: loads issued, results never consumed
-        float d0[ITER], d1[ITER], d2[ITER], d3[ITER];
-        fold3_load<ITER>(w, p.L, p.T, tbase, ks * Cfg::BK + 2 * c, lin_mask, d0, d1, d2, d3);
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) x0[i] = x1[i] = y0[i] = y1[i] = 1.f;
-        return;
-      }
       fold3_load<ITER>(w, p.L, p.T, tbase, ks * Cfg::BK + 2 * c, lin_mask, x0, x1, y0, y1);
     };
     // fold + split the loaded samples of step g and write the bf16 pairs into the step's stage

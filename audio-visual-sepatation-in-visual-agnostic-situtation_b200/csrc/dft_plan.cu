@@ -652,7 +652,7 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     const char* env_pw = getenv("AVSEP_DFT_FOLD3_GROUPS");
     pl->fold3_sets = (env_pw && atoi(env_pw) == 1) ? 1 : 2;
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
-    pl->fold_prefetch = env_pf ? atoi(env_pf) : 1;
+    pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
     std::vector<uint16_t> fb;
     fill_basis_fold(fb);
     PLAN_CUDA(cudaMalloc(&pl->basis_fold, fb.size() * 2));
