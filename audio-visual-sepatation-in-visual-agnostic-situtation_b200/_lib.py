@@ -49,6 +49,8 @@ SIGNATURES = {
     "avsep_plan_set_fold": (_I, [_P, _I]),
     "avsep_plan_set_two_cta": (_I, [_P, _I]),
     "avsep_plan_set_fused_stage": (_I, [_P, _I, _I]),
+    "avsep_plan_set_mix_linear": (_I, [_P, _I]),
+    "avsep_stft_mix": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "avsep_stft": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "avsep_separate": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P]),
     "avsep_istft": (_I, [_P, _P, _P, _I, _P, _P]),

@@ -815,4 +815,311 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
   }
 }
 
+
+// ======================================================================================================
+// dft_fold3m: dft_fold3 for a MIXTURE THAT IS THE SUM OF ITS TWO SOURCES (dataset/music.py:127 builds every training
+// mixture that way).  The STFT is linear, so the mixture spectrum is X0 + X1 and only the two source transforms are
+// computed: a third less tensor work, waveform traffic and operand conversion than three transforms.
+// Pair tile = 256 bins x 128 frames of BOTH sources of one mixture: four 128-column accumulators
+// [source 0 Re | source 0 Im | source 1 Re | source 1 Im] fill the 512 TMEM columns, the B tiles of a stage hold the
+// CTA's 64 frames of source 0 in rows 0..63 and of source 1 in rows 64..127 (same 64 KB stage, same producer code),
+// the MMAs run with N = 128 per source, and the epilogue writes three magnitude planes
+// |X0 + X1|, |X0|, |X1| -- the [mixture | source 0 | source 1] layout the rest of the step reads.
+// ======================================================================================================
+constexpr int FOLD3M_TILE_N = 128;
+
+template <int NG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD3_THREADS, 1)
+dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p) {
+  using Cfg = Fold3Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* xpose_all = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 2));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int n_tiles = (p.T + FOLD3M_TILE_N - 1) / FOLD3M_TILE_N;
+  const int nmix = p.num_signals;                  // mixtures; signal planes of p.mag: [mixture | source 0 | source 1] x nmix
+  const int pair_tiles = p.num_signals * n_tiles * (FOLD_M_TILES / 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + 2 * (FOLD3_PW / NG));   // TMA expect_tx arrival + the producer warps of the step's group, both CTAs
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 512);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp < 4) {
+  // warpgroup 0 (TMA warp, MMA warp, two idle warps) hands registers to the producer warpgroup
+  setmaxnreg_dec<48>();
+  if (warp == 0) {
+    // ===================================== TMA producer: basis rows (both CTAs) ================
+    // All 32 lanes first pull the waveform segment of a tile's 128 frames (135 KB, contiguous) into L2, one tile
+    // ahead of the producer warps, so their loads never wait on DRAM.
+    auto prefetch_tile = [&](int tile) {
+      if (!p.prefetch || tile >= pair_tiles) return;
+      const int rest = tile / (FOLD_M_TILES / 2);
+      const int nt = rest % n_tiles;
+      const int b = rest / n_tiles;
+      const int t_first = nt * FOLD3M_TILE_N + (int)rank * (FOLD3M_TILE_N / 2);
+      const int lo = max(t_first * AVSEP_HOP - AVSEP_N_FFT / 2, 0);
+      const int hi = min((t_first + FOLD3M_TILE_N / 2 - 1) * AVSEP_HOP + AVSEP_N_FFT / 2, p.L - 1);
+      for (int src = 0; src < 2; ++src) {
+        const float* w = p.wave + ((size_t)src * nmix + b) * p.L;
+        const char* bb = reinterpret_cast<const char*>(w + lo);
+        const char* e = reinterpret_cast<const char*>(w + hi + 1);
+        bb -= reinterpret_cast<uintptr_t>(bb) & 127u;
+        for (const char* q = bb + lane * 128; q < e; q += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+      }
+    };
+    prefetch_tile(pair);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < pair_tiles; tile += npairs) {
+      prefetch_tile(tile + npairs);
+      if (lane == 0) {
+        const int mp = tile % (FOLD_M_TILES / 2);
+        const int row0 = (2 * mp + (int)rank) * FOLD_TILE_M;
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 41);
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * 4 * Cfg::SUB_BYTES);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma2_load_2d(&tmA, lead_full, st + j * Cfg::SUB_BYTES, ks * Cfg::BK, j * FOLD_BINS + row0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, FOLD3M_TILE_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_phase = 0;
+      for (int tile = pair; tile < pair_tiles; tile += npairs) {
+        mbar_wait(tempty_bar, tile_phase ^ 1u, p.err_flag, 42);
+        tcgen05_fence_after();
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 43);
+          tcgen05_fence_after();
+          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int src = 0; src < 2; ++src) {
+#pragma unroll
+            for (int kind = 0; kind < 2; ++kind) {
+              // accumulators: [source 0 Re | source 0 Im | source 1 Re | source 1 Im], 128 columns (frames) each
+              const uint32_t d_tmem = tmem_base + (uint32_t)((2 * src + kind) * FOLD3M_TILE_N);
+              const uint32_t brow = (uint32_t)(src * (FOLD3M_TILE_N / 2) * Cfg::ROW_BYTES);   // this source's 64 rows of the B tiles
+              const uint64_t a_hi = umma_smem_desc(st + (2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+              const uint64_t a_lo = umma_smem_desc(st + (2 * kind + 1) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+              const uint64_t b_hi = umma_smem_desc(st + (4 + 2 * kind) * Cfg::SUB_BYTES + brow, Cfg::ROW_BYTES);
+              const uint64_t b_lo = umma_smem_desc(st + (5 + 2 * kind) * Cfg::SUB_BYTES + brow, Cfg::ROW_BYTES);
+#pragma unroll
+              for (int k16 = 0; k16 < Cfg::BK / 16; ++k16) {
+                const uint64_t adv = (uint64_t)(k16 * 2);
+                umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+                umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+          }
+          umma_commit_2sm(empty_bar(stage), 3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar, 3);
+        tile_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  }
+  } else if (warp >= 12) {
+    // ===================================== operand producers: waveform -> E / O hi / lo tiles ==
+    constexpr int WPG = FOLD3_PW / NG;                 // warps per group
+    constexpr int RPW = FOLD3M_TILE_N / WPG;           // rows per producer warp (16 or 32) of the CTA's 2 sources x 64 frames
+    constexpr int ITER = RPW / 2;                      // a warp covers 2 rows x 32 samples per iteration
+    setmaxnreg_inc<104>();
+    const int grp = (warp - 12) / WPG;
+    const int pw = (warp - 12) % WPG;
+    const int sub = lane >> 4, c = lane & 15;
+    const int r0 = pw * RPW;
+    const int my_tiles = pair < pair_tiles ? (pair_tiles - pair + npairs - 1) / npairs : 0;
+    const int steps = my_tiles * Cfg::KSTEPS;
+    float a0[ITER], a1[ITER], b0[ITER], b1[ITER];
+    const float* w = p.wave;
+    int tbase = 0, tile_i = -1;
+    uint32_t lin_mask = 0;
+    auto issue_loads = [&](int g, float (&x0)[ITER], float (&x1)[ITER], float (&y0)[ITER], float (&y1)[ITER], int& tb) {
+      const int ks = g % Cfg::KSTEPS;                  // g = flat (tile, k step) index of this pair, increasing
+      if (g / Cfg::KSTEPS != tile_i) {
+        tile_i = g / Cfg::KSTEPS;
+        const int tile = pair + tile_i * npairs;
+        const int rest = tile / (FOLD_M_TILES / 2);
+        const int nt = rest % n_tiles;
+        const int b = rest / n_tiles;
+        w = p.wave + ((size_t)(r0 / (FOLD3M_TILE_N / 2)) * nmix + b) * p.L;                 // rows 0..63: source 0, 64..127: source 1
+        tbase = nt * FOLD3M_TILE_N + (int)rank * (FOLD3M_TILE_N / 2) + r0 % (FOLD3M_TILE_N / 2) + sub;
+        // bit i: both frames of iteration i lie in [2, (L - 512) / 256], where no sample index leaves the signal
+        lin_mask = 0;
+        const int t_even = tbase - sub;
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+          const int t = t_even + 2 * i;
+          if (t >= 2 && (t + 1) * AVSEP_HOP + AVSEP_N_FFT / 2 <= p.L - 1 && t + 1 < p.T) lin_mask |= 1u << i;
+        }
+      }
+      tb = tbase;
+      fold3_load<ITER>(w, p.L, p.T, tbase, ks * Cfg::BK + 2 * c, lin_mask, x0, x1, y0, y1);
+    };
+    // fold + split the loaded samples of step g and write the bf16 pairs into the step's stage
+    auto convert_store = [&](int g, const float (&x0)[ITER], const float (&x1)[ITER], const float (&y0)[ITER],
+                             const float (&y1)[ITER], int tb) {
+      const int stage = g % Cfg::STAGES;
+      const uint32_t phase = (uint32_t)(g / Cfg::STAGES) & 1u;
+      const int n0 = (g % Cfg::KSTEPS) * Cfg::BK + 2 * c;
+      const bool pair0 = n0 >= 1, pair1 = n0 + 1 <= AVSEP_N_FFT / 2 - 1;
+      mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 44);   // the MMAs that read the stage's previous contents are done
+      uint8_t* bt = smem_gen + stage * Cfg::STAGE_BYTES + 4 * Cfg::SUB_BYTES;
+      // Fast path (14 of 16 K steps of a full tile): every frame exists and every sample has its mirror partner, so
+      // no masking.  The generic path handles K step 0 (n = 0 has no partner), K step 15 (n = 511) and ragged tiles.
+      const bool plain = (n0 - 2 * c) != 0 && (n0 - 2 * c) != (Cfg::KSTEPS - 1) * Cfg::BK && tb - sub + RPW <= p.T;
+      auto emit = [&](int i, float E0, float E1, float O0, float O1) {
+        const int r = r0 + 2 * i + sub;
+        // SWIZZLE_64B: the 16-byte chunk index (address bits 4..5) is XORed with address bits 7..8 = (r >> 1) & 3
+        const int off = r * Cfg::ROW_BYTES + ((4 * c) ^ ((((r0 >> 1) + i) & 3) << 4));
+        const __nv_bfloat162 eh = __floats2bfloat162_rn(E0, E1);
+        const float2 ehf = __bfloat1622float2(eh);
+        const __nv_bfloat162 el = __floats2bfloat162_rn(E0 - ehf.x, E1 - ehf.y);
+        const __nv_bfloat162 oh = __floats2bfloat162_rn(O0, O1);
+        const float2 ohf = __bfloat1622float2(oh);
+        const __nv_bfloat162 ol = __floats2bfloat162_rn(O0 - ohf.x, O1 - ohf.y);
+        *reinterpret_cast<__nv_bfloat162*>(bt + off) = eh;
+        *reinterpret_cast<__nv_bfloat162*>(bt + Cfg::SUB_BYTES + off) = el;
+        *reinterpret_cast<__nv_bfloat162*>(bt + 2 * Cfg::SUB_BYTES + off) = oh;
+        *reinterpret_cast<__nv_bfloat162*>(bt + 3 * Cfg::SUB_BYTES + off) = ol;
+      };
+      if (plain) {
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) emit(i, x0[i] + y0[i], x1[i] + y1[i], x0[i] - y0[i], x1[i] - y1[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+          const bool ok = tb + 2 * i < p.T;            // frames past the end of a ragged clip are zero rows
+          const float u0 = ok ? x0[i] : 0.f, u1 = ok ? x1[i] : 0.f;
+          const float v0 = (ok && pair0) ? y0[i] : 0.f, v1 = (ok && pair1) ? y1[i] : 0.f;
+          emit(i, u0 + v0, u1 + v1, pair0 ? u0 - v0 : 0.f, pair1 ? u1 - v1 : 0.f);
+        }
+      }
+      fence_proxy_async_smem();                        // generic-proxy stores -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(full_bar(stage), 0));
+    };
+    int tb = 0;
+    if (grp < steps) issue_loads(grp, a0, a1, b0, b1, tb);
+    for (int g = grp; g < steps; g += NG) {
+      convert_store(g, a0, a1, b0, b1, tb);
+      // refill AFTER the store: its fence.proxy.async would otherwise wait for these loads
+      if (g + NG < steps) issue_loads(g + NG, a0, a1, b0, b1, tb);
+    }
+  } else {
+    // ===================================== epilogue (8 warps per CTA, own 128 bins) ===========
+    setmaxnreg_inc<112>();
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t lead_tempty = mapa_shared(tempty_bar, 0);
+    uint32_t tile_phase = 0;
+    for (int tile = pair; tile < pair_tiles; tile += npairs) {
+      const int mp = tile % (FOLD_M_TILES / 2);
+      const int rest = tile / (FOLD_M_TILES / 2);
+      const int nt = rest % n_tiles;
+      const int b = rest / n_tiles;
+      mbar_wait(tfull_bar, tile_phase, p.err_flag, 45);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;
+      float* xt = xpose_all + (warp - 4) * (32 * 33);
+      // which = 0: mixture = |X0 + X1| (the STFT is linear and the mixture IS the sum of its sources), 1 / 2: |X0| / |X1|
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+        const int t0 = nt * FOLD3M_TILE_N + c0;
+        if (t0 >= p.T) break;
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+#pragma unroll
+          for (int h16 = 0; h16 < 2; ++h16) {
+            const uint32_t col = taddr + (uint32_t)(c0 + 16 * h16);
+            uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
+            if (which != 2) {
+              tmem_ld_32x32b_x16(col, r0v);
+              tmem_ld_32x32b_x16(col + FOLD3M_TILE_N, i0v);
+            }
+            if (which != 1) {
+              tmem_ld_32x32b_x16(col + 2 * FOLD3M_TILE_N, r1v);
+              tmem_ld_32x32b_x16(col + 3 * FOLD3M_TILE_N, i1v);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float rr, ii;
+              if (which == 0) {
+                rr = __uint_as_float(r0v[j]) + __uint_as_float(r1v[j]);
+                ii = __uint_as_float(i0v[j]) + __uint_as_float(i1v[j]);
+              } else if (which == 1) {
+                rr = __uint_as_float(r0v[j]);
+                ii = __uint_as_float(i0v[j]);
+              } else {
+                rr = __uint_as_float(r1v[j]);
+                ii = __uint_as_float(i1v[j]);
+              }
+              xt[lane * 33 + 16 * h16 + j] = sqrtf(fmaf(rr, rr, ii * ii));
+            }
+          }
+          __syncwarp();
+          const int t = t0 + lane;
+          if (t < p.T) {
+            float* dst = p.mag + ((size_t)(which * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T + t;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) __stcs(dst + (size_t)r * p.T, xt[r * 33 + lane]);
+          }
+          __syncwarp();
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive_cluster_relaxed(lead_tempty);
+      tile_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 }  // namespace avsep

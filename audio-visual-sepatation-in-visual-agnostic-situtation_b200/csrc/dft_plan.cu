@@ -296,6 +296,7 @@ struct avsep_plan {
   CUtensorMap tm_basis_fold, tm_fold;
   CUtensorMap tm_basis_fold32;          // the same basis with 32-column SWIZZLE_64B boxes (dft_fold3)
   bool fused_stage = true;              // dft_fold3: E / O operand generated inside the GEMM, no staging kernel
+  bool mix_linear = true;               // two-source device-summed mixtures: |X0 + X1| from the two source transforms (dft_fold3m)
   int fold3_sets = 2;                   // producer groups of dft_fold3 (1: all warps on every K step, 2: alternate K steps)
   const float* last_wave = nullptr;     // arguments of the last forward transform, for avsep_debug_gemm_only
   int last_mix_B = 0, last_mix_N = 0;
@@ -457,6 +458,20 @@ static int launch_fold3(avsep_plan* pl, const FoldParams& prm, int grid2, cudaSt
 
 // mixtures summed on the device (mix_N > 0) keep the staged path: wave_fold_kernel sums the sources while staging
 static bool use_fold3(const avsep_plan* pl, int mix_N = 0) { return pl->fold && pl->two_cta && pl->fused_stage && mix_N == 0; }
+
+// forward transform of a device-summed two-source mixture batch (see dft_fold3m in dft_fold.cuh)
+template <int NG>
+static int launch_fold3m(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
+  const int n_tiles = ceil_div(prm.T, FOLD3M_TILE_N);
+  const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
+  const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+  if (grid2 <= 0) return AVSEP_OK;
+  auto kern = dft_fold3m_fwd_kernel<NG>;
+  AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
+  kern<<<grid2, FOLD3_THREADS, Fold3Cfg::SMEM_BYTES, stream>>>(pl->tm_basis_fold32, prm);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
 
 static int launch_fold(avsep_plan* pl, FoldParams prm, cudaStream_t stream) {
   if (prm.wave != nullptr) {
@@ -649,6 +664,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     pl->fold_chunk = env_ch ? atoi(env_ch) : 0;     // measured: chunking is neutral (0.584 ms/step either way), so one launch pair
     const char* env_fs = getenv("AVSEP_DFT_FUSED_STAGE");
     pl->fused_stage = !(env_fs && atoi(env_fs) == 0);
+    const char* env_ml = getenv("AVSEP_DFT_MIX_LINEAR");
+    pl->mix_linear = !(env_ml && atoi(env_ml) == 0);
     const char* env_pw = getenv("AVSEP_DFT_FOLD3_GROUPS");
     pl->fold3_sets = (env_pw && atoi(env_pw) == 1) ? 1 : 2;
     const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
@@ -719,6 +736,12 @@ int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int groups) {
   return AVSEP_OK;
 }
 
+int avsep_plan_set_mix_linear(avsep_plan* pl, int enable) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_mix_linear: plan is null");
+  pl->mix_linear = enable != 0;
+  return AVSEP_OK;
+}
+
 int avsep_plan_set_two_cta(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_two_cta: plan is null");
   pl->two_cta = enable != 0;
@@ -747,6 +770,19 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   pl->last_wave = wave_dev;
   pl->last_mix_B = mix_B;
   pl->last_mix_N = mix_N;
+  if (use_fold3(pl) && pl->mix_linear && mix_N == 2 && S == 3 * mix_B && !phase_dev && !re_dev) {
+    // magnitudes of [mixture | source 0 | source 1] from TWO transforms: the mixture is the sum of its sources
+    FoldParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.num_signals = mix_B;
+    fp.T = pl->T;
+    fp.mag = mag_dev;
+    fp.prefetch = pl->fold_prefetch;
+    fp.err_flag = pl->err_flag;
+    fp.wave = wave_dev;
+    fp.L = pl->wave_len;
+    return pl->fold3_sets == 2 ? launch_fold3m<2>(pl, fp, stream) : launch_fold3m<1>(pl, fp, stream);
+  }
   if (pl->fold) {
     // Optional chunking (AVSEP_DFT_FOLD_CHUNK = signals per chunk, e.g. 74 = two rounds of pair tiles): the staged
     // E / O planes of a chunk (1 MB per signal) are then consumed by the GEMM right after they are written and
@@ -796,6 +832,11 @@ extern "C" {
 int avsep_stft(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev,
                float* im_dev, void* stream) {
   return stft_impl(pl, wave_dev, S, mag_dev, phase_dev, re_dev, im_dev, S, stream, 0, 0);
+}
+
+int avsep_stft_mix(avsep_plan* pl, const float* sources_dev, int B, int N, float* mag_dev, float* phase_dev, void* stream) {
+  AVSEP_REQUIRE(B >= 0 && N >= 1 && N <= AVSEP_MAX_SRC, "avsep_stft_mix: bad B = %d / N = %d", B, N);
+  return stft_impl(pl, sources_dev, (N + 1) * B, mag_dev, phase_dev, nullptr, nullptr, 0, stream, B, N);
 }
 
 int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const float* mag_dev, const float* phase_dev,

@@ -265,6 +265,11 @@ class Step:
         self.T = 1 + wave_len // ops.HOP
         self.out_len = ops.HOP * (self.T - 1)
 
+    @property
+    def plan(self) -> "ops.Plan":
+        """The step's STFT / iSTFT plan (borrowed): kernel-variant switches such as plan.set_mix_linear(False)."""
+        return ops.Plan.borrowed(lib.avsep_step_plan(self._h))
+
     def set_graph(self, enable: bool = True):
         """Replay the train step as a CUDA graph (captured on the 2nd call with unchanged arguments; side streams only)."""
         check(lib.avsep_step_set_graph(self._h, int(bool(enable))), "avsep_step_set_graph")

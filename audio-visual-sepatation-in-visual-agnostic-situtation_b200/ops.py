@@ -71,6 +71,17 @@ class Plan:
         self.frames = int(lib.avsep_plan_frames(h))
         self.istft_len = int(lib.avsep_plan_istft_len(h))
 
+    @classmethod
+    def borrowed(cls, handle) -> "Plan":
+        """Non-owning view of a plan that lives inside another object (avsep_step_plan); close() does nothing."""
+        import ctypes as C
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(handle) if isinstance(handle, int) else handle
+        self._borrowed = True
+        self.frames = int(lib.avsep_plan_frames(self._h))
+        self.istft_len = int(lib.avsep_plan_istft_len(self._h))
+        return self
+
     @property
     def handle(self):
         return self._h
@@ -84,6 +95,9 @@ class Plan:
     def set_fused_stage(self, enable: bool, groups: int = 0) -> None:
         check(lib.avsep_plan_set_fused_stage(self._h, int(bool(enable)), int(groups)), "avsep_plan_set_fused_stage")
 
+    def set_mix_linear(self, enable: bool) -> None:
+        check(lib.avsep_plan_set_mix_linear(self._h, int(bool(enable))), "avsep_plan_set_mix_linear")
+
     def set_two_cta(self, enable: bool) -> None:
         check(lib.avsep_plan_set_two_cta(self._h, int(bool(enable))), "avsep_plan_set_two_cta")
 
@@ -91,9 +105,9 @@ class Plan:
         check(lib.avsep_plan_set_fold(self._h, int(enable)), "avsep_plan_set_fold")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and not getattr(self, "_borrowed", False):
             lib.avsep_plan_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -152,6 +166,24 @@ def stft(wave: torch.Tensor, *, phase: bool = True, complex_parts: bool = False,
         mag, ph = mag[0], (ph[0] if ph is not None else None)
         re, im = (re[0] if re is not None else None), (im[0] if im is not None else None)
     return (mag, ph, re, im) if complex_parts else (mag, ph)
+
+
+def stft_mix(sources: torch.Tensor, *, phase: bool = False, plan: Optional[Plan] = None):
+    """STFT magnitudes of B mixtures and their N sources from the sources alone [N, B, L]: returns
+    (mag [(N+1), B, 512, T] with index 0 = the mixture = sum of the sources, phase | None).  The batched form of
+    BaseDataset._mix_n_and_stft (dataset/base.py:174-189, mixture built at dataset/music.py:127); with N = 2 and no
+    phase only the two source transforms run (the mixture spectrum is their sum)."""
+    w = _cuda_f32(sources, "stft_mix: sources")
+    if w.dim() != 3:
+        raise _lib.AvsepError(f"stft_mix: sources must be [N, B, L], got shape {tuple(sources.shape)}")
+    N, B, L = w.shape
+    pl = plan or get_plan((N + 1) * B, L)
+    T = pl.frames
+    mag = torch.empty(((N + 1) * B, N_BINS, T), device=w.device, dtype=torch.float32)
+    ph = torch.empty_like(mag) if phase else None
+    check(lib.avsep_stft_mix(pl.handle, w.data_ptr(), B, N, mag.data_ptr(), _p(ph), _stream()), "avsep_stft_mix")
+    shape = (N + 1, B, N_BINS, T)
+    return mag.view(shape), (ph.view(shape) if ph is not None else None)
 
 
 def istft(mag: torch.Tensor, phase: torch.Tensor, *, plan: Optional[Plan] = None) -> torch.Tensor:

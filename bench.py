@@ -255,14 +255,24 @@ def main_ours(args, rank, world, local):
     step = av.Step(B, N, K, L)
     step.set_graph(not args.no_graph)                              # train step replayed as a CUDA graph (side streams only)
     eval_mode = args.workload == "eval"
+    if not eval_mode and not args.explicit_mixture:
+        step.set_mix_on_device(True)
     main_stream = torch.cuda.Stream()                              # graphs cannot be captured on the legacy default stream
     torch.cuda.set_stream(main_stream)
     wav_dev = torch.empty((B, N + 1, 65280), device=dev) if eval_mode else None
     wav_host = torch.empty((B, N + 1, 65280)).pin_memory() if eval_mode else None
 
+    # Train step: the step is handed the SOURCE waveforms only and forms the mixture on the GPU, as the e2e arm does
+    # (dataset/music.py:127 defines the mixture as the sum of its sources); --explicit-mixture hands over the
+    # mixture waveform as a third signal instead.
+    src_only = not eval_mode and not args.explicit_mixture
+    sources_dev = waves_dev[1:]                                    # [N, B, L] view
+
     def step_dev():
         if eval_mode:
             step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        elif src_only:
+            step.train_dev(sources_dev, vecs_dev, feat, scale, bias, dfeat, dvecs, dscale, dbias, loss)
         else:
             step.train_dev(waves_dev, vecs_dev, feat, scale, bias, dfeat, dvecs, dscale, dbias, loss)
 
@@ -362,7 +372,8 @@ def main_ours(args, rank, world, local):
         for p in pipes:
             p["step"].set_mix_on_device(False)
         assert abs(loss_host - loss_val) <= 1e-6 * max(abs(loss_val), 1.0), (loss_host, loss_val)
-        assert abs(loss_host_full - loss_val) <= 1e-6 * max(abs(loss_val), 1.0), (loss_host_full, loss_val)
+        # explicit mixture waveform vs |X0 + X1|: equal to fp32 rounding of the magnitudes (a few binary targets may flip)
+        assert abs(loss_host_full - loss_val) <= 1e-4 * max(abs(loss_val), 1.0), (loss_host_full, loss_val)
     for _ in range(40):                                            # keep the GPU loaded until a few more samples land
         step_dev()
     torch.cuda.synchronize()
@@ -426,8 +437,12 @@ def main_ours(args, rank, world, local):
         mw = av._lib.ptr_array([outs[3 + n].data_ptr() for n in range(N)])
         gg = av._lib.ptr_array([outs[3 + N + n].data_ptr() for n in range(N)])
         chk = av._lib.check
-        t_stft = time_calls(lambda: chk(lib.avsep_stft(plan, waves_dev.data_ptr(), S, mag.data_ptr(), None, None, None, stream)), 10)
-        t_gemm = time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan, 0, S, mag.data_ptr(), stream)), 10)
+        if src_only:                                 # one kernel: two source transforms, mixture spectrum = their sum
+            t_stft = time_calls(lambda: chk(lib.avsep_stft_mix(plan, sources_dev.data_ptr(), B, N, mag.data_ptr(), None, stream)), 10)
+            t_gemm = t_stft
+        else:
+            t_stft = time_calls(lambda: chk(lib.avsep_stft(plan, waves_dev.data_ptr(), S, mag.data_ptr(), None, None, None, stream)), 10)
+            t_gemm = time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan, 0, S, mag.data_ptr(), stream)), 10)
         t_prep = time_calls(lambda: chk(lib.avsep_prepare(mag.data_ptr(), mags, N, B, T, 1, 1, 1, outs[0].data_ptr(), mw,
                                                           outs[1].data_ptr(), outs[2].data_ptr(), gg, stream)), 10)
         t_fwd = time_calls(lambda: chk(lib.avsep_synth_forward(feat.data_ptr(), vecs_dev.data_ptr(), scale.data_ptr(), bias.data_ptr(),
@@ -453,11 +468,13 @@ def main_ours(args, rank, world, local):
             if a["bound"] == "tensor":
                 ach = a["flops"] * B / (ms * 1e-3) / 1e12
                 kernels.append(dict(kernel=name, ms=ms, share=ms / tot, bound="tensor", achieved=ach, peak=pk["tensor"],
-                                    unit="TFLOP/s", frac=ach / pk["tensor"], executed_tflops=1.5 * ach,
-                                    tensor_pipe_frac=1.5 * ach / pk["tensor"],
+                                    unit="TFLOP/s", frac=ach / pk["tensor"], executed_tflops=(1.0 if src_only else 1.5) * ach,
+                                    tensor_pipe_frac=(1.0 if src_only else 1.5) * ach / pk["tensor"],
                                     note="algorithmic = fp32-equivalent full DFT (0.536 GFLOP/signal); executed = bf16x3 "
                                          "split on the folded (half-size) contraction = 1.5x algorithmic; with fused "
-                                         "staging (dft_fold3) this one kernel also folds / splits the waveform"))
+                                         "staging (dft_fold3) this one kernel also folds / splits the waveform; when the "
+                                         "step forms the mixture from its 2 sources (default) only 2 of the 3 transforms "
+                                         "are executed (mixture spectrum = X0 + X1), i.e. executed = 1.0x algorithmic"))
             else:
                 ach = a["bytes"] * B / (ms * 1e-3) / 1e9
                 kernels.append(dict(kernel=name, ms=ms, share=ms / tot, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s",
@@ -493,6 +510,10 @@ def main_ours(args, rank, world, local):
                         batch_per_gpu=B, global_batch=B * world, num_mix=N, K=K, samples=L, stft="1022/256", grid="256x256",
                         parallelism=f"batch-sharded x{world}, no data-path collective", numa_node_rank0=numa_node,
                         launch=("plain launches" if args.no_graph or eval_mode else "CUDA graph replay of the step's kernels (see gpu_launches / steps)"),
+                        mixture=("n/a" if eval_mode else
+                                 "explicit mixture waveform, 3 transforms" if args.explicit_mixture else
+                                 "formed on the GPU from the 2 device-resident source waveforms (dataset/music.py:127): mixture "
+                                 "spectrum = X0 + X1, 2 transforms executed"),
                         l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                      pipeline_depth=pipe_depth, timer="host wall clock around the K steps, synchronised on both sides",
@@ -519,6 +540,9 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain kernel launches instead of CUDA-graph replay of the step")
+    ap.add_argument("--explicit-mixture", action="store_true",
+                    help="train workload: hand the step the mixture waveform as a third signal instead of letting it form "
+                         "the mixture from the sources on the GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

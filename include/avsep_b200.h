@@ -78,6 +78,13 @@ size_t avsep_plan_workspace_bytes(const avsep_plan* plan);
 int avsep_stft(avsep_plan* plan, const float* wave_dev, int S,
                float* mag_dev, float* phase_dev, float* re_dev, float* im_dev, void* stream);
 
+/* STFT of B mixtures given only their N sources (the hand-off of dataset/music.py:120-127, where the mixture IS the
+ * sum of the sources): sources_dev [N, B, L] -> mag_dev [(N+1) B, 512, T] with the mixtures in planes [0, B) and source
+ * n in planes [(1+n) B, (2+n) B); phase_dev (same layout) is optional.  The mixture waveform is never materialised:
+ * with N = 2 and no phase output the mixture spectrum is taken as X0 + X1 (avsep_plan_set_mix_linear), otherwise the
+ * staging kernel sums the sources on the fly.  Replaces BaseDataset._mix_n_and_stft (dataset/base.py:174-189) per batch. */
+int avsep_stft_mix(avsep_plan* plan, const float* sources_dev, int B, int N, float* mag_dev, float* phase_dev, void* stream);
+
 /* K4. Replaces the reconstruction loop of calc_metrics (main.py:213-249) + utils.istft_reconstruction
  * (utils.py:101-104): un-warp each predicted mask 256->512 bins (grid_sample with warpgrid(warp=False)),
  * threshold (> mask_thres) if binary, multiply the mixture spectrum, inverse DFT (tcgen05 GEMM),
@@ -121,6 +128,12 @@ int avsep_plan_set_two_cta(avsep_plan* plan, int enable);
  * groups: 1 = all producer warps work on every K step, 2 = two groups alternate K steps (default, measured
  * slightly faster on B200), 0 keeps the setting. */
 int avsep_plan_set_fused_stage(avsep_plan* plan, int enable, int groups);
+/* enable = 1 (default): when a step forms the mixture on the device as the sum of its N = 2 sources
+ * (avsep_step_set_mix_on_device; dataset/music.py:127 defines every training mixture that way) and only magnitudes
+ * are needed (training), the mixture spectrum is taken as X0 + X1 -- the STFT is linear -- so two transforms are
+ * computed instead of three (dft_fold3m).  0: the mixture waveform is summed and transformed like any other signal.
+ * The two routes agree to fp32 rounding (tests/test_gpu_step.py). */
+int avsep_plan_set_mix_linear(avsep_plan* plan, int enable);
 /* selects the K-block of the GEMM pipeline: 16 (32B swizzle, 9 stages), 32 (64B swizzle, 4 stages) or
  * 64 (128B swizzle, 2 stages) */
 int avsep_plan_set_kblock(avsep_plan* plan, int kblock);

@@ -166,6 +166,35 @@ def test_fused_stage_equals_staged_operand(warps, length):
     plan.close()
 
 
+@pytest.mark.parametrize("N,B,length", [(2, 3, L), (2, 2, 70001), (2, 1, 3000), (3, 2, L)])
+def test_stft_mix_from_sources(N, B, length):
+    """avsep_stft_mix: magnitudes of the mixtures and sources from the sources alone.  N = 2 takes the linear route
+    (dft_fold3m: |X0 + X1| from two transforms); N = 3 and the phase output sum the waveform while staging."""
+    g = np.random.default_rng(N * 100 + B)
+    src = np.stack([_signals(B, seed=int(g.integers(1 << 20)), length=length) for _ in range(N)]) / N      # [N, B, L]
+    mag, _ = av.stft_mix(torch.from_numpy(src).cuda())
+    mixw = src.sum(axis=0).astype(np.float32)
+    ref_mix, _ = av.stft(torch.from_numpy(mixw).cuda(), phase=False)
+    ref_src, _ = av.stft(torch.from_numpy(src.reshape(N * B, length)).cuda(), phase=False)
+    _sync()
+    scale = float(ref_mix.max())
+    assert float((mag[0] - ref_mix).abs().max()) / scale < 2e-5
+    assert float((mag[1:].reshape(N * B, 512, -1) - ref_src).abs().max()) / scale < 2e-6
+    for b in range(B):
+        assert relerr(mag[0, b].cpu().numpy(), O.stft_magphase(mixw[b])[0]) < TOL
+    if N == 2:                                                    # with the linear route switched off: the summed waveform's own transform
+        plan = av.Plan(3 * B, length)
+        plan.set_mix_linear(False)
+        m2, p2 = av.stft_mix(torch.from_numpy(src).cuda(), plan=plan)
+        assert torch.equal(m2[0], ref_mix)
+        m3, p3 = av.stft_mix(torch.from_numpy(src).cuda(), phase=True, plan=plan)
+        _sync()
+        rec = m3[0, 0].cpu().numpy().astype(np.float64) * np.exp(1j * p3[0, 0].cpu().numpy().astype(np.float64))
+        spec = O.stft_complex(mixw[0])
+        assert np.max(np.abs(rec - spec)) / np.max(np.abs(spec)) < TOL
+        plan.close()
+
+
 def test_stft_golden_fixture(golden):
     g = golden("stft")
     src = O.synth_sources(1, 2, seed=1234)[0]

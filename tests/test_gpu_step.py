@@ -110,6 +110,9 @@ def test_train_step_vs_oracle():
     st.set_fused_train(True)
     # mixture formed on the GPU from the N sources (dataset/music.py:127): same bits for N = 2 (one IEEE add)
     st.set_mix_on_device(True)
+    st.plan.set_mix_linear(False)                                # the summed waveform goes through its own transform
+    mag_ref = st.buffer("mag")
+    gt_ref = st.buffer("gt_masks")
     loss3 = torch.empty(1, device="cuda")
     dfeat3 = torch.empty_like(dfeat)
     st.train_dev(c(np.ascontiguousarray(waves[1:])), c(vecs), tfeat, c(scale), c(bias), dfeat3, None, None, None, loss3)
@@ -117,6 +120,25 @@ def test_train_step_vs_oracle():
     assert float(loss3) == float(loss) and torch.equal(dfeat3, dfeat)
     lh2 = st.train_host(torch.from_numpy(np.ascontiguousarray(waves[1:])).pin_memory(), vh, tfeat, c(scale), c(bias), dfeat2, dv_host)
     assert lh2 == float(loss)
+    # default: the STFT is linear, so the mixture spectrum is X0 + X1 and only the two sources are transformed
+    # (dft_fold3m).  Same magnitudes to fp32 rounding; a binary ground-truth mask may flip only where
+    # mag_n / mag_mix sits within that rounding of 0.5.
+    st.plan.set_mix_linear(True)
+    loss5 = torch.empty(1, device="cuda")
+    dfeat5 = torch.empty_like(dfeat)
+    st.train_dev(c(np.ascontiguousarray(waves[1:])), c(vecs), tfeat, c(scale), c(bias), dfeat5, None, None, None, loss5)
+    torch.cuda.synchronize()
+    mag5 = st.buffer("mag")
+    assert float((mag5 - mag_ref).abs().max()) / float(mag_ref.max()) < 2e-5
+    assert torch.equal(mag5[B:], mag_ref[B:]) or float((mag5[B:] - mag_ref[B:]).abs().max()) / float(mag_ref.max()) < 2e-6
+    for b in range(B):
+        assert relerr(mag5[b].cpu().numpy(), O.stft_magphase(waves[0, b])[0]) < TOL          # mixture magnitude vs the oracle
+    flipped = int((st.buffer("gt_masks") != gt_ref).sum())
+    assert flipped <= 2e-4 * gt_ref.numel(), flipped
+    assert abs(float(loss5) - float(loss)) < 1e-4 * abs(float(loss))
+    same = (st.buffer("gt_masks") == gt_ref).all(dim=0)                                       # [B,1,256,T] pixels with identical targets
+    d5, d0 = dfeat5 * same, dfeat * same
+    assert float((d5 - d0).abs().max()) / float(d0.abs().max()) < 1e-4
     st.set_mix_on_device(False)
     st.close()
 
