@@ -310,14 +310,26 @@ class Step:
             raise _lib.AvsepError(f"Step.buffer: no buffer named {name}")
         return torch.as_tensor(_DevView(int(ptr), shape), device="cuda").clone()
 
-    # waves: [N+1, B, L] (index 0 = mixture); vecs [B,N,K]; feat [B,K,256,T] (device)
+    def _check_waves(self, waves, what):
+        """The C-ABI takes raw pointers: a [N, B, L] sources tensor handed to a step that expects [N+1, B, L] (or the
+        reverse) would be read past its end, so the element count is checked here."""
+        signals = self.N if getattr(self, "mix_on_device", False) else self.N + 1
+        need = signals * self.B * self.L
+        if waves.numel() != need or waves.dtype != torch.float32 or not waves.is_contiguous():
+            raise _lib.AvsepError(f"{what}: waves must be contiguous float32 [{signals}, {self.B}, {self.L}] "
+                                  f"({'sources only: the mixture is formed on the GPU' if signals == self.N else 'index 0 = mixture'}), "
+                                  f"got shape {tuple(waves.shape)} {waves.dtype}")
+
+    # waves: [N+1, B, L] (index 0 = mixture), or [N, B, L] sources after set_mix_on_device(True); vecs [B,N,K]; feat [B,K,256,T]
     def train_dev(self, waves, vecs, feat, scale, bias, dfeat, dvecs=None, dscale=None, dbias=None, loss=None):
+        self._check_waves(waves, "Step.train_dev")
         check(lib.avsep_step_train_dev(self._h, waves.data_ptr(), vecs.data_ptr(), feat.data_ptr(), ops._p(scale), ops._p(bias),
                                        ops._p(dfeat), ops._p(dvecs), ops._p(dscale), ops._p(dbias), ops._p(loss), ops._stream()),
               "avsep_step_train_dev")
 
     def train_host(self, waves_host, vecs_host, feat, scale, bias, dfeat, dvecs_host=None):
         """Host buffers in (pinned CPU tensors), loss out as a python float; H2D / D2H inside the call."""
+        self._check_waves(waves_host, "Step.train_host")
         loss = np.zeros(1, dtype=np.float32)
         check(lib.avsep_step_train_host(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
                                         ops._p(bias), ops._p(dfeat), ops._p(dvecs_host), loss.ctypes.data, ops._stream()),
@@ -327,15 +339,18 @@ class Step:
     def train_host_async(self, waves_host, vecs_host, feat, scale, bias, dfeat, loss_host, dvecs_host=None):
         """Enqueue H2D + step + D2H on the current stream and return; loss_host (pinned, 1 float) is valid after the
         stream is synchronised.  Two Steps on two streams overlap the copy of step i+1 with the kernels of step i."""
+        self._check_waves(waves_host, "Step.train_host_async")
         check(lib.avsep_step_train_host_async(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
                                               ops._p(bias), ops._p(dfeat), ops._p(dvecs_host), loss_host.data_ptr(), ops._stream()),
               "avsep_step_train_host_async")
 
     def eval_dev(self, waves, vecs, feat, scale, bias, wav=None, binary_mask=True, mask_thres=0.5):
+        self._check_waves(waves, "Step.eval_dev")
         check(lib.avsep_step_eval_dev(self._h, waves.data_ptr(), vecs.data_ptr(), feat.data_ptr(), ops._p(scale), ops._p(bias),
                                       int(binary_mask), float(mask_thres), ops._p(wav), ops._stream()), "avsep_step_eval_dev")
 
     def eval_host(self, waves_host, vecs_host, feat, scale, bias, wav_host, binary_mask=True, mask_thres=0.5):
+        self._check_waves(waves_host, "Step.eval_host")
         check(lib.avsep_step_eval_host(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
                                        ops._p(bias), int(binary_mask), float(mask_thres), wav_host.data_ptr(), ops._stream()),
               "avsep_step_eval_host")

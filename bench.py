@@ -371,6 +371,7 @@ def main_ours(args, rank, world, local):
     if not eval_mode:
         for p in pipes:
             p["step"].set_mix_on_device(False)
+        step.set_mix_on_device(src_only)             # pipes[0] is the value arm's Step: back to the input layout step_dev() passes
         assert abs(loss_host - loss_val) <= 1e-6 * max(abs(loss_val), 1.0), (loss_host, loss_val)
         # explicit mixture waveform vs |X0 + X1|: equal to fp32 rounding of the magnitudes (a few binary targets may flip)
         assert abs(loss_host_full - loss_val) <= 1e-4 * max(abs(loss_val), 1.0), (loss_host_full, loss_val)
