@@ -109,7 +109,8 @@ int avsep_istft(avsep_plan* plan, const float* mag_dev, const float* phase_dev, 
  * operands currently staged in the plan: out_dev [S, 1024, T] fp32, row order = basis row order. */
 int avsep_debug_raw_gemm(avsep_plan* plan, int inverse, int S, float* out_dev, void* stream);
 /* Same, but with the product epilogue (forward: mag [S,512,T]; inverse: wav [S, 256*(T-1)]): the GEMM
- * kernel alone on already-staged operands, so it can be timed in isolation. */
+ * kernel alone on already-staged operands, so it can be timed in isolation.  With fused staging (the default) the
+ * forward kernel has no staged operand: it re-reads the waveform pointer of the last avsep_stft call on this plan. */
 int avsep_debug_gemm_only(avsep_plan* plan, int inverse, int S, float* out_dev, void* stream);
 /* copies the bf16 hi/lo basis (as fp32 sums) to host: out_host [1024, 1024] */
 int avsep_debug_basis(avsep_plan* plan, int inverse, float* out_host);
@@ -124,7 +125,8 @@ int avsep_plan_set_two_cta(avsep_plan* plan, int enable);
 /* enable = 1 (default, needs fold and two_cta): the folded GEMM builds its E / O operand inside the kernel from the
  * fp32 waveform (8 producer warps per CTA fold, split to bf16 hi / lo and write the swizzled shared-memory tiles the
  * tensor core reads), so no staging kernel runs and no staged planes cross HBM; 0: wave_fold_kernel stages the planes
- * and dft_fold2 reads them by TMA (also what runs whenever the mixture is summed on the device).
+ * and dft_fold2 reads them by TMA (also what runs when a mixture summed on the device has N != 2 sources or needs
+ * phase / (re, im) outputs; the N = 2 magnitude-only case has its own fused kernel, see avsep_plan_set_mix_linear).
  * groups: 1 = all producer warps work on every K step, 2 = two groups alternate K steps (default, measured
  * slightly faster on B200), 0 keeps the setting. */
 int avsep_plan_set_fused_stage(avsep_plan* plan, int enable, int groups);
