@@ -14,7 +14,12 @@ plan = av.Plan(S, L)
 mag = torch.empty(S, 512, 256, device="cuda")
 lib, chk = av._lib.lib, av._lib.check
 st = torch.cuda.current_stream().cuda_stream
-call = lambda: chk(lib.avsep_stft(plan._h, w.data_ptr(), S, mag.data_ptr(), None, None, None, st))
+if os.environ.get("MIX"):                        # two sources per mixture, mixture spectrum = X0 + X1 (dft_fold3m)
+    Bm = S // 3
+    src = w[:2 * Bm].reshape(2, Bm, L)
+    call = lambda: chk(lib.avsep_stft_mix(plan._h, src.data_ptr(), Bm, 2, mag.data_ptr(), None, st))
+else:
+    call = lambda: chk(lib.avsep_stft(plan._h, w.data_ptr(), S, mag.data_ptr(), None, None, None, st))
 for _ in range(5):
     call()
 torch.cuda.synchronize()
