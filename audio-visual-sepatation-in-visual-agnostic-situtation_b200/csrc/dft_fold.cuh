@@ -820,10 +820,10 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
 // dft_fold3m: dft_fold3 for a MIXTURE THAT IS THE SUM OF ITS TWO SOURCES (dataset/music.py:127 builds every training
 // mixture that way).  The STFT is linear, so the mixture spectrum is X0 + X1 and only the two source transforms are
 // computed: a third less tensor work, waveform traffic and operand conversion than three transforms.
-// Pair tile = 256 bins x 128 frames of BOTH sources of one mixture: four 128-column accumulators
-// [source 0 Re | source 0 Im | source 1 Re | source 1 Im] fill the 512 TMEM columns, the B tiles of a stage hold the
-// CTA's 64 frames of source 0 in rows 0..63 and of source 1 in rows 64..127 (same 64 KB stage, same producer code),
-// the MMAs run with N = 128 per source, and the epilogue writes three magnitude planes
+// Pair tile = 256 bins x 128 frames of BOTH sources of one mixture.  The B tiles of a stage hold the CTA's 64 frames
+// of source 0 in rows 0..63 and of source 1 in rows 64..127 (same 64 KB stage, same producer code as dft_fold3), one
+// N = 256 MMA per product covers both sources, so the Re (TMEM columns [0, 256)) and Im ([256, 512)) accumulators
+// hold [CTA0: source 0 | source 1 | CTA1: source 0 | source 1] x 64 frames, and the epilogue writes three magnitude planes
 // |X0 + X1|, |X0|, |X1| -- the [mixture | source 0 | source 1] layout the rest of the step reads.
 // ======================================================================================================
 constexpr int FOLD3M_TILE_N = 128;
@@ -918,7 +918,7 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =======================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, FOLD3M_TILE_N);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, 2 * FOLD3M_TILE_N);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_phase = 0;
@@ -929,24 +929,22 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
           mbar_wait(full_bar(stage), phase, p.err_flag, 43);
           tcgen05_fence_after();
           const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
+          // One N = 256 MMA per product covers BOTH sources: the B tile's 128 rows per CTA are [source 0: 64 frames |
+          // source 1: 64 frames], so accumulator columns come out as [CTA0: src0 | src1 | CTA1: src0 | src1] x 64 frames.
+          // (Two N = 128 MMAs, one per source, would read the basis tile from shared memory twice.)
 #pragma unroll
-          for (int src = 0; src < 2; ++src) {
+          for (int kind = 0; kind < 2; ++kind) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(kind * 2 * FOLD3M_TILE_N);               // Re: columns [0, 256), Im: [256, 512)
+            const uint64_t a_hi = umma_smem_desc(st + (2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+            const uint64_t a_lo = umma_smem_desc(st + (2 * kind + 1) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+            const uint64_t b_hi = umma_smem_desc(st + (4 + 2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
+            const uint64_t b_lo = umma_smem_desc(st + (5 + 2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
 #pragma unroll
-            for (int kind = 0; kind < 2; ++kind) {
-              // accumulators: [source 0 Re | source 0 Im | source 1 Re | source 1 Im], 128 columns (frames) each
-              const uint32_t d_tmem = tmem_base + (uint32_t)((2 * src + kind) * FOLD3M_TILE_N);
-              const uint32_t brow = (uint32_t)(src * (FOLD3M_TILE_N / 2) * Cfg::ROW_BYTES);   // this source's 64 rows of the B tiles
-              const uint64_t a_hi = umma_smem_desc(st + (2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
-              const uint64_t a_lo = umma_smem_desc(st + (2 * kind + 1) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
-              const uint64_t b_hi = umma_smem_desc(st + (4 + 2 * kind) * Cfg::SUB_BYTES + brow, Cfg::ROW_BYTES);
-              const uint64_t b_lo = umma_smem_desc(st + (5 + 2 * kind) * Cfg::SUB_BYTES + brow, Cfg::ROW_BYTES);
-#pragma unroll
-              for (int k16 = 0; k16 < Cfg::BK / 16; ++k16) {
-                const uint64_t adv = (uint64_t)(k16 * 2);
-                umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
-                umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-                umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-              }
+            for (int k16 = 0; k16 < Cfg::BK / 16; ++k16) {
+              const uint64_t adv = (uint64_t)(k16 * 2);
+              umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+              umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
           umma_commit_2sm(empty_bar(stage), 3);
@@ -1071,15 +1069,17 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
         for (int which = 0; which < 3; ++which) {
 #pragma unroll
           for (int h16 = 0; h16 < 2; ++h16) {
-            const uint32_t col = taddr + (uint32_t)(c0 + 16 * h16);
+            // frame c0 + 16 h16 + j of the pair tile belongs to CTA `half` (64 frames each): source 0 sits in columns
+            // half * 128 + (frame % 64), source 1 64 columns further; Im is 256 columns after Re
+            const uint32_t col = taddr + (uint32_t)(half * 2 * (FOLD3M_TILE_N / 2) + (c0 - half * (FOLD3M_TILE_N / 2)) + 16 * h16);
             uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
             if (which != 2) {
               tmem_ld_32x32b_x16(col, r0v);
-              tmem_ld_32x32b_x16(col + FOLD3M_TILE_N, i0v);
+              tmem_ld_32x32b_x16(col + 2 * FOLD3M_TILE_N, i0v);
             }
             if (which != 1) {
-              tmem_ld_32x32b_x16(col + 2 * FOLD3M_TILE_N, r1v);
-              tmem_ld_32x32b_x16(col + 3 * FOLD3M_TILE_N, i1v);
+              tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2, r1v);
+              tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2 + 2 * FOLD3M_TILE_N, i1v);
             }
             tmem_ld_wait();
 #pragma unroll
