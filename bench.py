@@ -60,6 +60,27 @@ ALG = {
 }
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a kernel, from the committed `ncu --set full` summary
+    (profiles/r1_ncu_full_summary.txt, produced by tools/ncu_summary.py); None if the kernel is not in it."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.txt")
+    if not os.path.exists(path):
+        return None
+    tot, inside, seen = 0.0, False, 0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(path):
+        if line.startswith("kernel:"):
+            if inside and seen:
+                break
+            inside = kernel_substr in line
+        elif inside and ("dram__bytes_read.sum " in line or "dram__bytes_write.sum " in line):
+            parts = line.split()
+            if len(parts) >= 3 and parts[-1] in scale:
+                tot += float(parts[-2]) * scale[parts[-1]]
+                seen += 1
+    return tot if seen == 2 else None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -422,7 +443,10 @@ def main_ours(args, rank, world, local):
                 kernels.append(dict(kernel=name, ms=ms, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"]))
         top = max(kernels, key=lambda k: k["ms"])
         roofline = dict(kernel=top["kernel"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"],
-                        frac=top["frac"], traffic=None, peak_source=pk["source"])
+                        frac=top["frac"], traffic=ncu_traffic({"dft_gemm_inv": "dft_gemm2_kernel", "spec_prep": "spec_prep_kernel",
+                                                               "dft_gemm_fwd": "dft_fold3_fwd_kernel"}.get(top["kernel"], top["kernel"])),
+                        traffic_unit="bytes per launch (dram read + write), ncu --set full: profiles/r1_ncu_full_summary.txt",
+                        peak_source=pk["source"])
     if rank == 0 and not eval_mode:
         lib, stream = av._lib.lib, torch.cuda.current_stream().cuda_stream
         plan = lib.avsep_step_plan(step._h)
@@ -486,7 +510,11 @@ def main_ours(args, rank, world, local):
                                 frac=ach / pk["hbm"], note="not part of the step: the unfused forward / backward pair, for comparison"))
         top = max([k for k in kernels if k["share"] is not None], key=lambda k: k["ms"])
         roofline = dict(kernel=top["kernel"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"],
-                        frac=top["frac"], traffic=None, peak_source=pk["source"],
+                        frac=top["frac"], traffic=ncu_traffic({"synth_train": "synth_train_kernel", "dft_gemm_fwd": "dft_fold3m_fwd_kernel",
+                                                               "prepare": "prepare_vec_kernel"}.get(top["kernel"], top["kernel"])),
+                        traffic_unit="bytes per launch (dram read + write), ncu --set full: profiles/r1_ncu_full_summary.txt",
+                        algorithmic_bytes_per_launch=(ALG[top["kernel"]].get("bytes", 0) * B or None),
+                        peak_source=pk["source"],
                         note=("algorithmic fp32-equivalent FLOPs (0.536 GFLOP/signal)" if top["bound"] == "tensor" else
                               "algorithmic bytes per SURVEY.md section 8(d) (feat_sound counted once: fused fwd+bwd)"))
 
