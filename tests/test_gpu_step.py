@@ -143,6 +143,28 @@ def test_train_step_vs_oracle():
     st.close()
 
 
+def test_step_rejects_wrong_waveform_layout():
+    """The C-ABI takes raw pointers, so the Python wrapper checks that the waveform tensor matches the step's input
+    layout ([N+1, B, L] with the mixture, or [N, B, L] sources after set_mix_on_device) instead of reading past its end."""
+    B, N, K = 1, 2, 32
+    waves, feat, vecs, scale, bias = _inputs(B, N, K, seed=5)
+    c = lambda a: torch.from_numpy(a).cuda()
+    st = av.Step(B, N, K, L)
+    dfeat = torch.empty((B, K, 256, 256), device="cuda")
+    with pytest.raises(av.AvsepError):
+        st.train_dev(c(np.ascontiguousarray(waves[1:])), c(vecs), c(feat), c(scale), c(bias), dfeat)      # sources only, mixture expected
+    st.set_mix_on_device(True)
+    with pytest.raises(av.AvsepError):
+        st.train_dev(c(waves), c(vecs), c(feat), c(scale), c(bias), dfeat)                               # mixture given, sources expected
+    with pytest.raises(av.AvsepError):
+        st.train_host(torch.from_numpy(waves).double(), torch.from_numpy(vecs), c(feat), c(scale), c(bias), dfeat)
+    loss = torch.empty(1, device="cuda")
+    st.train_dev(c(np.ascontiguousarray(waves[1:])), c(vecs), c(feat), c(scale), c(bias), dfeat, None, None, None, loss)
+    torch.cuda.synchronize()
+    assert np.isfinite(float(loss))
+    st.close()
+
+
 def test_eval_step_vs_oracle_with_sdr():
     B, N, K = 2, 2, 32
     waves, feat, vecs, scale, bias = _inputs(B, N, K, seed=4321)
