@@ -9,7 +9,10 @@ S, L = 240, 65535
 lib, chk = av._lib.lib, av._lib.check
 w = (torch.rand((S, L), device="cuda") - 0.5)
 plan = av.Plan(S, L)
-mag, ph = av.stft(w, plan=plan)
+plan.set_fused_stage(False)                 # this sweep times the GEMM kernels on STAGED operands (the fused kernels have none)
+for fold in (0, 1):                         # stage both operand layouts once
+    plan.set_fold(fold)
+    mag, ph = av.stft(w, plan=plan)
 wav = av.istft(mag, ph, plan=plan)          # stages the inverse operand
 torch.cuda.synchronize()
 stream = torch.cuda.current_stream().cuda_stream
