@@ -497,18 +497,32 @@ synth_finalize_kernel(const float* __restrict__ s_partial, const float* __restri
   if (blk < K) {
     for (int i = threadIdx.x; i < B * N; i += blockDim.x) {       // i = b * N + n
       const int bb = i / N, n = i % N;
-      float t = 0.f;
-      for (int c = 0; c < chunks; ++c) t += s_partial[(((size_t)bb * chunks + c) * N + n) * Kp + blk];
+      // the per-CTA partials of one (b, n, k) are N * Kp floats apart: four independent accumulators keep four loads
+      // in flight (a single running sum made this kernel a chain of `chunks` L2 round trips: 12 us for 34 CTAs)
+      const float* sp = s_partial + ((size_t)bb * chunks * N + n) * Kp + blk;
+      const size_t cs = (size_t)N * Kp;
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      int c = 0;
+      for (; c + 4 <= chunks; c += 4) {
+        t0 += sp[(size_t)c * cs];
+        t1 += sp[(size_t)(c + 1) * cs];
+        t2 += sp[(size_t)(c + 2) * cs];
+        t3 += sp[(size_t)(c + 3) * cs];
+      }
+      for (; c < chunks; ++c) t0 += sp[(size_t)c * cs];
+      const float t = (t0 + t1) + (t2 + t3);
       if (dvecs) dvecs[(size_t)i * K + blk] = t * (scale ? scale[blk] : 1.f);
       acc += (double)(t * vecs[(size_t)i * K + blk]);
     }
     const double tot = block_sum<double>(acc, red);
     if (threadIdx.x == 0 && dscale) dscale[blk] = (float)tot;
   } else if (blk == K) {
+#pragma unroll 4
     for (int i = threadIdx.x; i < B * chunks * N; i += blockDim.x) acc += (double)dz_partial[i];
     const double tot = block_sum<double>(acc, red);
     if (threadIdx.x == 0 && dbias) dbias[0] = (float)tot;
   } else {
+#pragma unroll 4
     for (int i = threadIdx.x; i < n_loss; i += blockDim.x) acc += loss_partial[i];
     const double tot = block_sum<double>(acc, red);
     if (threadIdx.x == 0 && loss) loss[0] = (float)(tot * inv_count);
