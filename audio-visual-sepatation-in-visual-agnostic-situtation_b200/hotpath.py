@@ -5,7 +5,7 @@ B200 path by changing imports only.  See INTEGRATION.md.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, List, Optional
+from typing import Callable, Optional
 
 import numpy as np
 import torch

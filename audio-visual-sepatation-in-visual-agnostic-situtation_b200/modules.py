@@ -6,8 +6,6 @@ models/synthesizer_net.py and models/criterion.py; the arithmetic runs in the CU
 """
 from __future__ import annotations
 
-from itertools import permutations
-from typing import List, Sequence
 
 import torch
 import torch.nn as nn

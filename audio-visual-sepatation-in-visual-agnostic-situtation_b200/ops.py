@@ -7,7 +7,7 @@ csrc/*.cu behind the C-ABI.  Every op validates device / dtype / layout and rais
 from __future__ import annotations
 
 import threading
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 
