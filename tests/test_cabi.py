@@ -124,3 +124,16 @@ def test_clip_windows_and_assemble_roundtrip():
     w2 = av.clip_windows(x, 65535, 32768)
     y2 = av.assemble_windows(w2[:, :65280], 32768, L)
     assert torch.equal(y2[:L - 300], x[:L - 300])
+
+
+def test_bench_reads_ncu_traffic_from_committed_profile():
+    """bench.py fills roofline.traffic from profiles/r1_ncu_full_summary.txt (dram read + write of one launch)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.ncu_traffic("synth_train_kernel")
+    assert t is not None and 1.0e9 < t < 2.0e9            # 1.34 GB of feat / dfeat + masks, targets, weights
+    assert bench.ncu_traffic("dft_fold3m_fwd_kernel") is not None
+    assert bench.ncu_traffic("no_such_kernel") is None
