@@ -20,10 +20,24 @@ class AvsepError(RuntimeError):
 
 
 def _load() -> C.CDLL:
-    if not os.path.exists(LIB_PATH):
-        # Build in-tree once (needs nvcc); a missing library is otherwise a hard error.
-        from .build import build
-        build()
+    """Load the in-tree library, never a stale one: with nvcc present build() is consulted on every import (it returns
+    immediately when the source fingerprint matches); without nvcc (a GPU box that received the prebuilt .so) the
+    recorded fingerprint must equal the fingerprint of the sources that travelled with it."""
+    from . import build as _build
+    try:
+        _build._nvcc()
+        have_nvcc = True
+    except RuntimeError:
+        have_nvcc = False
+    if have_nvcc:
+        _build.build()
+    else:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing and nvcc is not available to build it (avsep_b200 has no CPU fallback)")
+        stamp = os.path.join(_build.OBJ_DIR, "fingerprint")
+        if not os.path.exists(stamp) or open(stamp).read() != _build._fingerprint():
+            raise ImportError(f"{LIB_PATH} was not built from the sources next to it (fingerprint mismatch) and nvcc is "
+                              "not available to rebuild it")
     return C.CDLL(LIB_PATH)
 
 
@@ -48,6 +62,7 @@ SIGNATURES = {
     "avsep_plan_set_kblock": (_I, [_P, _I]),
     "avsep_plan_set_fold": (_I, [_P, _I]),
     "avsep_plan_set_two_cta": (_I, [_P, _I]),
+    "avsep_plan_set_inverse_fold": (_I, [_P, _I]),
     "avsep_plan_set_fused_stage": (_I, [_P, _I, _I]),
     "avsep_plan_set_mix_linear": (_I, [_P, _I]),
     "avsep_stft_mix": (_I, [_P, _P, _I, _I, _P, _P, _P]),

@@ -7,6 +7,7 @@
 
 #include "dft_gemm.cuh"
 #include "dft_fold.cuh"
+#include "idft_fold.cuh"
 #include "warp_taps.h"
 
 namespace avsep {
@@ -305,6 +306,10 @@ struct avsep_plan {
   CUtensorMap tm_wave2, tm_spec2;       // same tensors, 128-frame boxes for the CTA-pair kernel
   bool two_cta = true;                  // cta_group::2 GEMM (one 256 x 256 tile per SM pair)
   bool tm_spec_valid = false;
+  int generation = 0;                   // bumped by every avsep_plan_set_*: captured CUDA graphs of a step are keyed on it
+  bool inverse_fold = true;             // inverse transform through the folded (half-work) GEMM (idft_fold.cuh)
+  __nv_bfloat16* basis_ifold = nullptr; // [4 = kind * 2 + split][512 rows in CTA-group order][512 bins]
+  CUtensorMap tm_basis_ifold, tm_spec_ifold;
   size_t workspace = 0;
 };
 
@@ -373,6 +378,13 @@ static int build_maps(avsep_plan* pl) {
     rc = encode_map(&pl->tm_fold, pl->fold_split, 3, dimsB, stridesB, boxB, fbk);
     if (rc) return rc;
   }
+  if (pl->basis_ifold) {
+    cuuint64_t dimsA[2] = {(cuuint64_t)IFOLD_K, (cuuint64_t)(4 * IFOLD_ROWS)};
+    cuuint64_t stridesA[1] = {(cuuint64_t)IFOLD_K * 2};
+    cuuint32_t boxA[2] = {(cuuint32_t)IFoldCfg::BK, 128};
+    int rc = encode_map(&pl->tm_basis_ifold, pl->basis_ifold, 2, dimsA, stridesA, boxA, IFoldCfg::BK);
+    if (rc) return rc;
+  }
   if (pl->spec_split) {
     cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
     cuuint64_t strides[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
@@ -381,6 +393,9 @@ static int build_maps(avsep_plan* pl) {
     if (rc) return rc;
     cuuint32_t box2[3] = {(cuuint32_t)bk, (cuuint32_t)(DFT_TILE_N / 2), 1};
     rc = encode_map(&pl->tm_spec2, pl->spec_split, 3, dims, strides, box2, bk);
+    if (rc) return rc;
+    cuuint32_t box3[3] = {(cuuint32_t)IFoldCfg::BK, (cuuint32_t)(IFOLD_TILE_N / 2), 1};
+    rc = encode_map(&pl->tm_spec_ifold, pl->spec_split, 3, dims, strides, box3, IFoldCfg::BK);
     if (rc) return rc;
     pl->tm_spec_valid = true;
   }
@@ -445,6 +460,49 @@ static void fill_basis_fold(std::vector<uint16_t>& out) {
         out[((size_t)(kind * 2 + 1) * FOLD_BINS + f) * FOLD_K + n] = lo;
       }
     }
+}
+
+// folded inverse basis (idft_fold.cuh): plane (kind * 2 + split), row R in CTA-group order, column = bin f
+static void fill_basis_ifold(std::vector<uint16_t>& out) {
+  const int NF = AVSEP_N_FFT;
+  out.assign((size_t)4 * IFOLD_ROWS * IFOLD_K, 0);
+  for (int R = 0; R < IFOLD_ROWS; ++R) {
+    const int n = ifold_row(R);
+    const double win = 0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)NF);
+    for (int f = 0; f < IFOLD_K; ++f) {
+      const bool edge = (f == 0 || f == NF / 2);
+      const double c = edge ? 1.0 : 2.0;
+      const int a = (int)(((long long)f * n) % NF);
+      const double ang = 2.0 * M_PI * (double)a / (double)NF;
+      // irfft ignores the imaginary part of the DC and Nyquist bins
+      const double vals[2] = {win * c * std::cos(ang) / (double)NF, edge ? 0.0 : -win * c * std::sin(ang) / (double)NF};
+      for (int kind = 0; kind < 2; ++kind) {
+        const float v = (float)vals[kind];
+        const uint16_t hi = host_f32_to_bf16(v);
+        const uint16_t lo = host_f32_to_bf16(v - host_bf16_to_f32(hi));
+        out[((size_t)(kind * 2 + 0) * IFOLD_ROWS + R) * IFOLD_K + f] = hi;
+        out[((size_t)(kind * 2 + 1) * IFOLD_ROWS + R) * IFOLD_K + f] = lo;
+      }
+    }
+  }
+}
+
+static int launch_ifold(avsep_plan* pl, int S, float* wav_dev, cudaStream_t stream) {
+  IFoldParams ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.num_signals = S;
+  ip.T = pl->T;
+  ip.lo_offset = pl->max_signals;
+  ip.wav = wav_dev;
+  ip.out_len = pl->out_len;
+  ip.inv_env = pl->inv_env;
+  ip.err_flag = pl->err_flag;
+  const int grid2 = 2 * std::min(2 * S, sm_count() / 2);
+  if (grid2 <= 0) return AVSEP_OK;
+  AVSEP_CUDA(cudaFuncSetAttribute(idft_fold2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IFoldCfg::SMEM_BYTES));
+  idft_fold2_kernel<<<grid2, IFOLD_THREADS, IFoldCfg::SMEM_BYTES, stream>>>(pl->tm_basis_ifold, pl->tm_spec_ifold, ip);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
 }
 
 template <int NG>
@@ -678,6 +736,13 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     PLAN_CUDA(cudaMalloc(&pl->fold_split, fold_elems * sizeof(__nv_bfloat16)));
     pl->workspace += fb.size() * 2 + fold_elems * sizeof(__nv_bfloat16);
   }
+  {
+    std::vector<uint16_t> ib;
+    fill_basis_ifold(ib);
+    PLAN_CUDA(cudaMalloc(&pl->basis_ifold, ib.size() * 2));
+    PLAN_CUDA(cudaMemcpy(pl->basis_ifold, ib.data(), ib.size() * 2, cudaMemcpyHostToDevice));
+    pl->workspace += ib.size() * 2;
+  }
   // staging buffer: large enough for either layout decision below
   {
     const size_t ov = (size_t)2 * max_signals * pl->Lpad;
@@ -711,6 +776,7 @@ int avsep_plan_destroy(avsep_plan* pl) {
   cudaFree(pl->spec_split);
   cudaFree(pl->inv_env);
   cudaFree(pl->basis_fold);
+  cudaFree(pl->basis_ifold);
   cudaFree(pl->fold_split);
   cudaFree(pl->err_flag);
   delete pl;
@@ -723,6 +789,7 @@ size_t avsep_plan_workspace_bytes(const avsep_plan* pl) { return pl ? pl->worksp
 
 int avsep_plan_set_fold(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fold: plan is null");
+  ++pl->generation;
   pl->fold = (enable & 1) != 0;
   pl->fold_prefetch = (enable & 2) ? 0 : 1;          // bit 1 set: folded GEMM without the L2 prefetch (A/B timing)
   return AVSEP_OK;
@@ -730,6 +797,7 @@ int avsep_plan_set_fold(avsep_plan* pl, int enable) {
 
 int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int groups) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fused_stage: plan is null");
+  ++pl->generation;
   AVSEP_REQUIRE(groups >= 0 && groups <= 2, "avsep_plan_set_fused_stage: groups must be 0 (keep), 1 or 2 (got %d)", groups);
   pl->fused_stage = enable != 0;
   if (groups) pl->fold3_sets = groups;
@@ -738,18 +806,28 @@ int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int groups) {
 
 int avsep_plan_set_mix_linear(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_mix_linear: plan is null");
+  ++pl->generation;
   pl->mix_linear = enable != 0;
+  return AVSEP_OK;
+}
+
+int avsep_plan_set_inverse_fold(avsep_plan* pl, int enable) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_inverse_fold: plan is null");
+  ++pl->generation;
+  pl->inverse_fold = enable != 0;
   return AVSEP_OK;
 }
 
 int avsep_plan_set_two_cta(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_two_cta: plan is null");
+  ++pl->generation;
   pl->two_cta = enable != 0;
   return AVSEP_OK;
 }
 
 int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_kblock: plan is null");
+  ++pl->generation;
   AVSEP_REQUIRE(kblock == 16 || kblock == 32 || kblock == 64, "avsep_plan_set_kblock: kblock must be 16, 32 or 64 (got %d)", kblock);
   AVSEP_CUDA(cudaDeviceSynchronize());
   pl->kblock = kblock;
@@ -759,6 +837,8 @@ int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
 }  // extern "C"
 
 namespace avsep {
+int plan_generation(const avsep_plan* pl) { return pl ? pl->generation : 0; }
+
 int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
               int reim_count, void* stream_, int mix_B, int mix_N) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_stft: plan is null");
@@ -886,6 +966,7 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
   dim3 grid(ceil_div(pl->T, 32), AVSEP_N_BINS / 64, B);
   spec_prep_kernel<<<grid, 256, 0, stream>>>(sp);
   AVSEP_LAUNCH_CHECK();
+  if (pl->inverse_fold) return launch_ifold(pl, B * nsig, wav_dev, stream);
   DftParams prm = base_params(pl, B * nsig);
   prm.wav = wav_dev;
   return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, stream, &pl->tm_spec2);
@@ -917,6 +998,7 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     int rc = ensure_spec(pl);
     if (rc) return rc;
     AVSEP_REQUIRE(pl->T <= DFT_TILE_N, "avsep_debug_gemm_only: inverse needs T <= %d", DFT_TILE_N);
+    if (pl->inverse_fold) return launch_ifold(pl, S, out_dev, (cudaStream_t)stream_);
     prm.wav = out_dev;
     return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, (cudaStream_t)stream_, &pl->tm_spec2);
   }

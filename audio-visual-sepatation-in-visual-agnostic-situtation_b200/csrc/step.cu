@@ -20,6 +20,7 @@ int synth_forward_impl(const float* feat, const float* vecs, const float* scale,
                        cudaStream_t stream);
 int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
               int reim_count, void* stream, int mix_B, int mix_N);
+int plan_generation(const avsep_plan* pl);
 bool synth_train_supported(int K, int HW, const float* dfeat);
 int synth_train_impl(const float* feat, const float* vecs, const float* scale, const float* bias, int B, int N, int K, int HW,
                      int act, int loss_kind, const float* gt, const float* weight, const float* gscale, float* pred, float* loss,
@@ -36,7 +37,7 @@ struct avsep_step {
   int no_fused_train = 0;     // debugging / A-B timing: run the separate forward and backward kernels
   int use_graph = 0;          // replay the train step as a CUDA graph (non-default streams only)
   cudaGraphExec_t graph_exec = nullptr;
-  const void* graph_key[12] = {};
+  const void* graph_key[13] = {};
   int graph_launches = 0;
   avsep_plan* plan = nullptr;
   float* waves = nullptr;     // [N+1, B, L]  (index 0 = mixture)
@@ -166,8 +167,10 @@ int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* ve
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!st->use_graph || stream == nullptr || stream == cudaStreamLegacy || stream == cudaStreamPerThread)
     return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
-  const void* key[12] = {waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev,
-                         (const void*)(uintptr_t)(st->mix_on_device * 2 + st->no_fused_train), (const void*)stream};
+  // the key also carries the plan's variant generation: avsep_plan_set_* after a capture must not replay the old kernels
+  const void* key[13] = {waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev,
+                         (const void*)(uintptr_t)(st->mix_on_device * 2 + st->no_fused_train), (const void*)stream,
+                         (const void*)(uintptr_t)plan_generation(st->plan)};
   if (st->graph_exec && memcmp(key, st->graph_key, sizeof(key)) == 0) {
     AVSEP_CUDA(cudaGraphLaunch(st->graph_exec, stream));
     count_launch(st->graph_launches);

@@ -74,13 +74,16 @@ def _mix_n_and_stft(audios, audio_mix, device="cuda"):
     audios: list of N numpy [L]; audio_mix numpy [L] -> (amp_mix [1,512,T], mags list of [1,512,T], phase_mix [1,512,T]);
     like the reference, `audios` entries are replaced by torch tensors."""
     N = len(audios)
-    stack = np.stack([np.asarray(audio_mix, dtype=np.float32)] + [np.asarray(a, dtype=np.float32) for a in audios])
-    w = torch.from_numpy(stack).to(device, non_blocking=True)
-    mag, _, re, im = ops.stft(w, phase=False, complex_parts=True)
-    phase_mix = torch.atan2(im[0], re[0])
+    mix = torch.from_numpy(np.ascontiguousarray(audio_mix, dtype=np.float32)[None]).to(device, non_blocking=True)
+    amp_mix, phase_mix = ops.stft(mix, phase=True)                 # |.| and angle from the kernel's epilogue (base.py:145-146)
+    mags = []
+    if N:
+        src = torch.from_numpy(np.stack([np.asarray(a, dtype=np.float32) for a in audios])).to(device, non_blocking=True)
+        amp_src, _ = ops.stft(src, phase=False)                    # the reference discards the sources' phase (base.py:181)
+        mags = [amp_src[n].unsqueeze(0) for n in range(N)]
     for n in range(N):
         audios[n] = torch.from_numpy(np.asarray(audios[n]))
-    return mag[0].unsqueeze(0), [mag[1 + n].unsqueeze(0) for n in range(N)], phase_mix.unsqueeze(0)
+    return amp_mix[0].unsqueeze(0), mags, phase_mix[0].unsqueeze(0)
 
 
 def stft_batch(audios: torch.Tensor, audio_mix: Optional[torch.Tensor] = None):
@@ -195,10 +198,15 @@ def calc_metrics(batch_data, outputs, args, get_metrics: Optional[Callable] = No
 # ------------------------------------------------------------------------------------------------
 # long-clip separation (BASELINE.json config C4)
 # ------------------------------------------------------------------------------------------------
-def clip_windows(audio: torch.Tensor, win: int = 65535, stride: int = 65535) -> torch.Tensor:
+RECON_LEN = 65280      # samples a 65535-sample window reconstructs: hop * (T - 1) = 256 * 255
+
+
+def clip_windows(audio: torch.Tensor, win: int = 65535, stride: int = RECON_LEN) -> torch.Tensor:
     """Cut a long clip [..., L] into windows [..., W, win]; the tail window is zero-padded, as the reference pads
     short clips (dataset/base.py:157-162).  The reference itself only ever processes one 6 s window
-    (inference.py:197-228); this is the defined extension to 60 s clips."""
+    (inference.py:197-228); this is the defined extension to 60 s clips.  The default stride is the length a window
+    RECONSTRUCTS (65280 = 256 * (T - 1), not its 65535 input samples), so the reconstructed windows tile the clip
+    without gaps."""
     L = audio.shape[-1]
     W = max(1, -(-max(L - win, 0) // stride) + 1)
     need = (W - 1) * stride + win
@@ -210,7 +218,8 @@ def clip_windows(audio: torch.Tensor, win: int = 65535, stride: int = 65535) -> 
 def assemble_windows(wavs: torch.Tensor, stride: int, total_len: int) -> torch.Tensor:
     """Inverse of clip_windows for reconstructed windows [W, ..., Lw] -> [..., total_len]: window i supplies the
     samples [i*stride, i*stride + min(stride, Lw)), the last window everything it has; no cross-fade (the
-    reference defines none).  Positions no window reconstructs (Lw = 65280 < stride = 65535) stay zero."""
+    reference defines none).  With stride <= Lw (the default 65280) every sample up to the end of the last window is
+    covered; a stride larger than Lw leaves the positions no window reconstructs at zero."""
     W, Lw = wavs.shape[0], wavs.shape[-1]
     out = wavs.new_zeros(wavs.shape[1:-1] + (total_len,))
     for i in range(W):
@@ -222,7 +231,7 @@ def assemble_windows(wavs: torch.Tensor, stride: int, total_len: int) -> torch.T
     return out
 
 
-def separate_long_clip(audio_mix: torch.Tensor, mask_fn: Callable, *, win: int = 65535, stride: int = 65535,
+def separate_long_clip(audio_mix: torch.Tensor, mask_fn: Callable, *, win: int = 65535, stride: int = RECON_LEN,
                        log_freq: bool = True, binary_mask: bool = True, mask_thres: float = 0.5,
                        rank: int = 0, world: int = 1) -> torch.Tensor:
     """Separate a long mixture [L] window by window on this rank's share of the windows.

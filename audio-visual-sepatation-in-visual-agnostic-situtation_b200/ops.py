@@ -101,6 +101,9 @@ class Plan:
     def set_two_cta(self, enable: bool) -> None:
         check(lib.avsep_plan_set_two_cta(self._h, int(bool(enable))), "avsep_plan_set_two_cta")
 
+    def set_inverse_fold(self, enable: bool) -> None:
+        check(lib.avsep_plan_set_inverse_fold(self._h, int(bool(enable))), "avsep_plan_set_inverse_fold")
+
     def set_fold(self, enable: bool) -> None:
         check(lib.avsep_plan_set_fold(self._h, int(enable)), "avsep_plan_set_fold")
 
@@ -357,7 +360,7 @@ class _SynthMasksLoss(torch.autograd.Function):
     recomputes dz from them (second pass over feat_sound)."""
 
     @staticmethod
-    def forward(ctx, feat, vecs, scale, bias, gt, weight, activation, loss_kind):
+    def forward(ctx, feat, vecs, scale, bias, gt, weight, activation, loss_kind, allow_fused=True):
         f = _cuda_f32(feat, "synth_loss: feat_sound")
         v = _cuda_f32(vecs, "synth_loss: vecs")
         s = _cuda_f32(scale, "synth_loss: scale") if scale is not None else None
@@ -370,7 +373,8 @@ class _SynthMasksLoss(torch.autograd.Function):
         empty = torch.empty(0, device=f.device)
         ctx.has_scale, ctx.has_bias, ctx.has_weight = s is not None, b is not None, w is not None
         ctx.activation, ctx.loss_kind = activation, loss_kind
-        ctx.fused = bool(ctx.needs_input_grad[0]) and K <= 32 and HW % 4 == 0
+        ctx.fused = bool(allow_fused) and bool(ctx.needs_input_grad[0]) and K <= 32 and HW % 4 == 0
+        ctx.consumed = False
         if ctx.fused:
             out = torch.empty((N, B) + tuple(f.shape[2:]), device=f.device, dtype=torch.float32)
             loss = torch.zeros((), device=f.device, dtype=torch.float32)
@@ -395,13 +399,22 @@ class _SynthMasksLoss(torch.autograd.Function):
         gs = _cuda_f32(gloss.reshape(1), "synth_loss backward: grad")
         need = ctx.needs_input_grad
         if ctx.fused:
+            # The saved buffers ARE the gradients (for an upstream gradient of 1) and are rescaled in place below, then
+            # handed to autograd, which may keep them as .grad without a copy.  A second backward over the same graph
+            # (retain_graph=True, a gradient penalty, two losses sharing err) would rescale them again -- g1 * g2 -- and
+            # alias what the first call returned, so it is refused instead of returning wrong gradients silently.
+            if ctx.consumed:
+                raise RuntimeError("synth_masks_loss: the fused training kernel's gradients were already consumed by an earlier "
+                                   "backward over this graph; call synth_masks_loss(..., fused=False) (separate, re-entrant "
+                                   "forward / backward kernels) when the graph is backpropagated more than once")
+            ctx.consumed = True
             dfeat, dvecs, dscale, dbias = ctx.saved_tensors
             outs = [dfeat, dvecs if need[1] else None, dscale if (ctx.has_scale and need[2]) else None,
                     dbias if (ctx.has_bias and need[3]) else None]
             for t in outs:
                 if t is not None:
                     check(lib.avsep_scale_if_needed(t.data_ptr(), t.numel(), gs.data_ptr(), _stream()), "avsep_scale_if_needed")
-            return outs[0], outs[1], outs[2], outs[3], None, None, None, None
+            return outs[0], outs[1], outs[2], outs[3], None, None, None, None, None
         f, v, s, out, g, w = ctx.saved_tensors
         s = s if ctx.has_scale else None
         w = w if ctx.has_weight else None
@@ -416,7 +429,7 @@ class _SynthMasksLoss(torch.autograd.Function):
         check(lib.avsep_synth_backward(f.data_ptr(), v.data_ptr(), _p(s), B, N, K, HW, ctx.activation, ctx.loss_kind,
                                        out.data_ptr(), g.data_ptr(), _p(w), gs.data_ptr(), None, _p(dfeat), _p(dvecs),
                                        _p(dscale), _p(dbias), scratch.data_ptr(), _stream()), "avsep_synth_backward")
-        return dfeat, dvecs, dscale, dbias, None, None, None, None
+        return dfeat, dvecs, dscale, dbias, None, None, None, None, None
 
 
 def _check_synth_shapes(feat, vecs, scale):
@@ -439,8 +452,13 @@ def synth_masks(feat_sound: torch.Tensor, vecs: torch.Tensor, scale: Optional[to
     return _SynthMasks.apply(feat_sound, vecs, scale, bias, ACTIVATIONS[activation])
 
 
-def synth_masks_loss(feat_sound, vecs, scale, bias, gt_masks, weight, *, loss: str = "bce", activation: str = "sigmoid"):
-    """Fused SoP++ step (SoP++/main.py:203-209): returns (err scalar, masks [N,B,*spatial] detached)."""
+def synth_masks_loss(feat_sound, vecs, scale, bias, gt_masks, weight, *, loss: str = "bce", activation: str = "sigmoid",
+                     fused: bool = True):
+    """Fused SoP++ step (SoP++/main.py:203-209): returns (err scalar, masks [N,B,*spatial] detached).
+
+    fused=True (default) lets the forward call run the one-pass training kernel when feat_sound needs a gradient; its
+    graph can be backpropagated ONCE (a second backward raises).  fused=False always uses the separate forward /
+    backward kernels, which read feat_sound twice but may be backpropagated any number of times (retain_graph)."""
     _check_synth_shapes(feat_sound, vecs, scale)
     if isinstance(gt_masks, (list, tuple)):
         gt_masks = torch.stack([g.reshape(g.shape[0], *feat_sound.shape[2:]) for g in gt_masks], dim=0)
@@ -451,7 +469,8 @@ def synth_masks_loss(feat_sound, vecs, scale, bias, gt_masks, weight, *, loss: s
         raise _lib.AvsepError("synth_masks_loss: weight must be [B,1,*spatial]")
     if loss not in ("bce", "l1", "l2"):
         raise Exception("Architecture undefined!")     # models/__init__.py:129
-    return _SynthMasksLoss.apply(feat_sound, vecs, scale, bias, gt_masks, weight, ACTIVATIONS[activation], LOSS_KINDS[loss])
+    return _SynthMasksLoss.apply(feat_sound, vecs, scale, bias, gt_masks, weight, ACTIVATIONS[activation], LOSS_KINDS[loss],
+                                 bool(fused))
 
 
 def synth_nosum(feat_img, feat_sound, scale, bias) -> torch.Tensor:

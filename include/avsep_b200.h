@@ -122,6 +122,11 @@ int avsep_plan_set_fold(avsep_plan* plan, int enable);
 /* enable = 1 (default): the plain DFT GEMM (inverse transform, and the forward one when fold is off) runs as CTA
  * pairs (tcgen05 cta_group::2, one 256 x 256 tile per two SMs); 0: one 128 x 256 tile per CTA. */
 int avsep_plan_set_two_cta(avsep_plan* plan, int enable);
+/* enable = 1 (default): the inverse transform of avsep_separate / avsep_istft (utils.py:101-104) runs as the FOLDED
+ * GEMM (csrc/idft_fold.cuh): irfft output symmetry y[n] = P[n] + Q[n], y[1022 - n] = P[n] - Q[n] turns the
+ * 1024 x 1024 contraction into two 512 x 512 ones (half the tensor work), overlap-add fused in the epilogue;
+ * 0: the plain 1024 x 1024 inverse DFT GEMM (kept as the in-library cross-check of the folded kernel). */
+int avsep_plan_set_inverse_fold(avsep_plan* plan, int enable);
 /* enable = 1 (default, needs fold and two_cta): the folded GEMM builds its E / O operand inside the kernel from the
  * fp32 waveform (8 producer warps per CTA fold, split to bf16 hi / lo and write the swizzled shared-memory tiles the
  * tensor core reads), so no staging kernel runs and no staged planes cross HBM; 0: wave_fold_kernel stages the planes
@@ -232,7 +237,12 @@ int avsep_pit_backward(int loss_kind, const float* preds_dev, const float* targe
 /* ---- end-to-end host-buffer entry points (what bench.py's `e2e` times) --------------------- */
 /* Config C2 train step through host buffers: H2D of the waveforms, STFT of all (N+1) signals,
  * prepare, synth + sigmoid + weighted BCE, full backward, D2H of the loss.
- *   waves_host [B, N+1, wave_len] (index 0 = mixture, pinned memory recommended)
+ *   waves_host [N+1, B, wave_len], SIGNAL-major: plane 0 = the B mixtures, plane 1+n = source n of every mixture
+ *              (pinned memory recommended); [N, B, wave_len] = the sources only after
+ *              avsep_step_set_mix_on_device(step, 1).  The same layout holds for waves_dev / waves_host of every
+ *              step entry point below (train_host, train_host_async, train_dev, eval_host, eval_dev).  A
+ *              mixture-major [B, N+1, wave_len] buffer has the same element count and would be accepted silently
+ *              with wrong mixture / source assignment: callers must transpose.
  *   vecs_host  [B, N, K]
  *   feat_dev   [B, K, 256*T] stays on the device (it is the U-Net's output in the reference and
  *              never exists on the host there); dfeat_dev [B,K,256*T] receives its gradient
@@ -262,9 +272,10 @@ int avsep_step_eval_host(avsep_step* step, const float* waves_host, const float*
 int avsep_step_eval_dev(avsep_step* step, const float* waves_dev, const float* vecs_dev,
                         const float* feat_dev, const float* scale_dev, const float* bias_dev,
                         int binary_mask, float mask_thres, float* wav_dev, void* stream);
-/* device views of the step's intermediates (valid until the next call): 0 mag [B*(N+1),512,T],
- * 1 mix re, 2 mix im [B,512,T], 3 mag_mix_w, 4 log_mag_mix, 5 weights [B,256,T], 6 gt [N,B,256,T],
- * 7 pred masks [N,B,256,T] */
+/* device views of the step's intermediates (valid until the next call): 0 mag [(N+1)*B,512,T] (signal-major like
+ * the waveforms), 1 mix re, 2 mix im [B,512,T], 3 mag_mix_w, 4 log_mag_mix, 5 weights [B,256,T], 6 gt [N,B,256,T],
+ * 7 pred masks [N,B,256,T], 8 loss [1], 9 dvecs [B,N,K], 10 dscale [K], 11 dbias [1], 12 warped source magnitudes
+ * [N,B,256,T], 13 wav [B,N+1,256*(T-1)] (eval steps); any other id returns NULL */
 const float* avsep_step_buffer(const avsep_step* step, int which);
 /* enable = 1: the `waves` argument of every step call holds only the N sources, [N, B, wave_len]; the mixture
  * (dataset/music.py:127: the sum of the sources) is formed on the GPU inside the staging kernel, which saves

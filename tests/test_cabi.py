@@ -108,18 +108,22 @@ def test_warpgrid_compat(golden):
 
 
 def test_clip_windows_and_assemble_roundtrip():
-    """Long-clip helper (config C4): 60 s @ 11025 Hz -> windows; stride 65535 -> 11 windows, stride 32768 -> 20."""
+    """Long-clip helper (config C4): 60 s @ 11025 Hz -> windows.  The default stride is what a window reconstructs
+    (65280 samples), so the assembled clip has no gaps; stride 32768 gives the overlapping secondary setting."""
     L = 661500
     x = torch.arange(L, dtype=torch.float32)
-    w = av.clip_windows(x, 65535, 65535)
-    assert w.shape == (11, 65535) and float(w[10, -1]) == 0.0 and float(w[1, 0]) == 65535.0
+    w = av.clip_windows(x)
+    assert w.shape == (11, 65535) and float(w[10, -1]) == 0.0 and float(w[1, 0]) == 65280.0
     assert av.clip_windows(x, 65535, 32768).shape[0] == 20
-    assert av.clip_windows(x[:1000], 65535, 65535).shape == (1, 65535)
-    # reconstruction windows are 65280 long: assemble puts each at its offset, gaps of 255 samples stay zero
+    assert av.clip_windows(x[:1000]).shape == (1, 65535)
+    # reconstruction windows are 65280 long and tile the clip seamlessly: gap-free round trip over the whole clip
     rec = w[:, :65280]
-    y = av.assemble_windows(rec, 65535, L)
-    assert torch.equal(y[:65280], x[:65280]) and float(y[65280:65535].abs().max()) == 0.0
-    assert torch.equal(y[65535:65535 + 65280], x[65535:65535 + 65280])
+    y = av.assemble_windows(rec, 65280, L)
+    assert torch.equal(y, x)
+    # an explicit stride of 65535 leaves the 255 samples no window reconstructs at zero
+    w_gap = av.clip_windows(x, 65535, 65535)
+    y_gap = av.assemble_windows(w_gap[:, :65280], 65535, L)
+    assert torch.equal(y_gap[:65280], x[:65280]) and float(y_gap[65280:65535].abs().max()) == 0.0
     # overlapping stride: later windows take over at their offset
     w2 = av.clip_windows(x, 65535, 32768)
     y2 = av.assemble_windows(w2[:, :65280], 32768, L)

@@ -255,6 +255,37 @@ def test_istft_vs_oracle():
     assert relerr(loud[0].cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize("length", [65535, 33000, 5000, 65535 - 256 * 3])
+def test_folded_inverse_equals_plain_inverse(length):
+    """The folded inverse GEMM (idft_fold.cuh: two 512 x 512 contractions + mirrored overlap-add) against the plain
+    1024 x 1024 inverse GEMM of the same library and against the fp64 oracle, at full and ragged frame counts."""
+    S = 3
+    wav = _signals(S, seed=21, length=length)
+    amp, ph = zip(*[O.stft_magphase(w) for w in wav])
+    amp, ph = np.stack(amp), np.stack(ph)
+    T = amp.shape[-1]
+    mask = (np.random.default_rng(5).random((S, 512, T)) > 0.3).astype(np.float32)
+    m, p_ = torch.from_numpy(amp * mask).cuda(), torch.from_numpy(ph).cuda()
+    pl = av.ops.Plan(S, length)
+    try:
+        assert pl.frames == T
+        pl.set_inverse_fold(True)
+        folded = av.istft(m, p_, plan=pl)
+        folded2 = av.istft(m, p_, plan=pl)
+        pl.set_inverse_fold(False)
+        plain = av.istft(m, p_, plan=pl)
+        _sync()
+    finally:
+        pl.close()
+    assert folded.shape == (S, 256 * (T - 1))
+    assert torch.equal(folded, folded2)                              # fixed summation order: bit-reproducible
+    scale = float(plain.abs().max())
+    assert float((folded - plain).abs().max()) / scale < 2e-5
+    for s in range(S):
+        ref = O.istft_reconstruction(amp[s] * mask[s], ph[s])
+        assert relerr(folded[s].cpu().numpy(), ref) < TOL
+
+
 def test_istft_golden_fixture(golden):
     g = golden("stft")
     src = O.synth_sources(1, 2, seed=1234)[0]
@@ -278,6 +309,54 @@ def test_istft_reconstruction_dropin():
     assert relerr(out, O.istft_reconstruction(amp, ph)) < TOL
     a2, p2 = av._stft(wav)
     assert a2.shape == (512, 256) and relerr(a2.cpu().numpy(), amp) < TOL
+
+
+def test_mix_n_and_stft_reference_signature():
+    """BaseDataset._mix_n_and_stft (dataset/base.py:174-189): list of N numpy sources + numpy mixture in,
+    (amp_mix [1,512,T], mags list of [1,512,T], phase_mix [1,512,T]) out; `audios` entries become torch tensors."""
+    N = 2
+    src = O.synth_sources(1, N, seed=31)[0]                      # [N, L]
+    mix = src.sum(axis=0).astype(np.float32)
+    audios = [src[n].copy() for n in range(N)]
+    amp_mix, mags, phase_mix = av._mix_n_and_stft(audios, mix)
+    _sync()
+    assert amp_mix.shape == (1, 512, 256) and phase_mix.shape == (1, 512, 256) and len(mags) == N
+    assert all(torch.is_tensor(a) and not a.is_cuda and a.shape == (L,) for a in audios)      # base.py:186-187
+    amp_o, ph_o = O.stft_magphase(mix)
+    assert relerr(amp_mix[0].cpu().numpy(), amp_o) < TOL
+    # the phase is ill-conditioned where the magnitude vanishes: compare the complex spectrum it reconstructs
+    spec = amp_mix[0].cpu().numpy() * np.exp(1j * phase_mix[0].cpu().numpy().astype(np.float64))
+    spec_o = amp_o * np.exp(1j * ph_o.astype(np.float64))
+    assert np.max(np.abs(spec - spec_o)) / np.max(np.abs(spec_o)) < TOL
+    for n in range(N):
+        assert mags[n].shape == (1, 512, 256)
+        assert relerr(mags[n][0].cpu().numpy(), O.stft_magphase(src[n])[0]) < TOL
+    # phase values themselves where the bin carries energy
+    strong = amp_o > 1e-2 * amp_o.max()
+    d = np.angle(np.exp(1j * (phase_mix[0].cpu().numpy()[strong].astype(np.float64) - ph_o[strong])))
+    assert np.max(np.abs(d)) < 1e-3
+
+
+def test_stft_batch_collated_form():
+    """stft_batch: collated [N,B,L] sources (+ optional mixture) -> the batch dict entries
+    mag_mix [B,1,512,T], mags list, phase_mix, equal to the per-item _mix_n_and_stft results."""
+    N, B = 2, 3
+    src = O.synth_sources(B, N, seed=32)                         # [B, N, L]
+    audios = torch.from_numpy(np.ascontiguousarray(src.transpose(1, 0, 2))).cuda()       # [N, B, L]
+    out = av.stft_batch(audios)
+    explicit = av.stft_batch(audios, audios.sum(dim=0))
+    _sync()
+    assert out["mag_mix"].shape == (B, 1, 512, 256) and out["phase_mix"].shape == (B, 1, 512, 256) and len(out["mags"]) == N
+    for k in ("mag_mix", "phase_mix"):
+        assert torch.equal(out[k], explicit[k])
+    for b in range(B):
+        mix = src[b].sum(axis=0).astype(np.float32)
+        amp_o, ph_o = O.stft_magphase(mix)
+        assert relerr(out["mag_mix"][b, 0].cpu().numpy(), amp_o) < TOL
+        spec = out["mag_mix"][b, 0].cpu().numpy() * np.exp(1j * out["phase_mix"][b, 0].cpu().numpy().astype(np.float64))
+        assert np.max(np.abs(spec - amp_o * np.exp(1j * ph_o.astype(np.float64)))) / np.max(amp_o) < TOL
+        for n in range(N):
+            assert relerr(out["mags"][n][b, 0].cpu().numpy(), O.stft_magphase(src[b, n])[0]) < TOL
 
 
 def _block_masks(rng, N, B, H=256, T=256, lo=0.2, hi=0.9, blk=8):

@@ -239,6 +239,76 @@ def test_synth_shapes_vs_oracle(N, K, H, W, use_scale):
             masks.sum().backward()                                # backward needs H*W % 4 == 0
 
 
+def test_forward_multi_equals_per_source_forward():
+    """InnerProd.forward_multi / Bias.forward_multi (one pass over feat_sound for all N sources) equal the reference's
+    per-source loop activate(net(ctx[:, n], feat), 'sigmoid') (SoP++/main.py:203-206), values and gradients."""
+    B, N, K, H, W = 2, 3, 32, 16, 24
+    g = np.random.default_rng(7)
+    feat = g.standard_normal((B, K, H, W)).astype(np.float32)
+    ctx = (1 / (1 + np.exp(-g.standard_normal((B, N, K))))).astype(np.float32)
+    for net in (av.InnerProd(K).cuda(), av.Bias().cuda()):
+        with torch.no_grad():
+            net.bias.fill_(0.2)
+            if hasattr(net, "scale"):
+                net.scale.copy_(_cuda((1 + 0.1 * g.standard_normal(K)).astype(np.float32)))
+        f1, c1 = _cuda(feat).requires_grad_(True), _cuda(ctx).requires_grad_(True)
+        multi = net.forward_multi(c1, f1, activation='sigmoid')
+        assert len(multi) == N and all(m.shape == (B, 1, H, W) for m in multi)
+        wsum = sum((n + 1.0) * multi[n].square().sum() for n in range(N))
+        wsum.backward()
+        grads_multi = [f1.grad.clone(), c1.grad.clone()] + [p_.grad.clone() for p_ in net.parameters()]
+        net.zero_grad()
+        f2, c2 = _cuda(feat).requires_grad_(True), _cuda(ctx).requires_grad_(True)
+        loop = [av.activate(net(c2[:, n], f2), 'sigmoid') for n in range(N)]
+        sum((n + 1.0) * loop[n].square().sum() for n in range(N)).backward()
+        grads_loop = [f2.grad, c2.grad] + [p_.grad for p_ in net.parameters()]
+        for n in range(N):
+            assert relerr(multi[n].detach().cpu().numpy(), loop[n].detach().cpu().numpy()) < 1e-6
+            z = np.einsum('bk,bkhw->bhw', ctx[:, n] * (net.scale.detach().cpu().numpy() if hasattr(net, "scale") else 1.0), feat) + 0.2
+            assert relerr(multi[n][:, 0].detach().cpu().numpy(), 1 / (1 + np.exp(-z))) < TOL
+        for a, b in zip(grads_multi, grads_loop):
+            assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+        net.zero_grad()
+
+
+def test_fused_loss_backward_twice():
+    """the fused training kernel's saved buffers are rescaled in place by backward, so a second backward over
+    the same graph must not silently return g1 * g2-scaled gradients: it raises; fused=False is re-entrant and returns
+    the correctly scaled gradients every time (non-unit upstream gradient, retain_graph)."""
+    B, N, K, H, W = 2, 2, 32, 8, 16
+    g = np.random.default_rng(11)
+    feat = g.standard_normal((B, K, H, W)).astype(np.float32)
+    vecs = (1 / (1 + np.exp(-g.standard_normal((B, N, K))))).astype(np.float32)
+    scale = (1 + 0.1 * g.standard_normal(K)).astype(np.float32)
+    bias = np.array([0.05], dtype=np.float32)
+    gts = [(g.random((B, 1, H, W)) > 0.5).astype(np.float32) for _ in range(N)]
+    wgt = np.clip(np.abs(g.standard_normal((B, 1, H, W))), 1e-3, 10).astype(np.float32)
+    o = O.synth_loss_and_grads("bce", feat, vecs, scale, bias, gts, wgt)
+
+    def leaves():
+        return (_cuda(feat).requires_grad_(True), _cuda(vecs).requires_grad_(True), _cuda(scale).requires_grad_(True),
+                _cuda(bias).requires_grad_(True))
+
+    tf, tv, ts, tb = leaves()
+    err, _ = av.synth_masks_loss(tf, tv, ts, tb, [_cuda(t) for t in gts], _cuda(wgt), loss="bce")
+    (3.0 * err).backward(retain_graph=True)
+    assert relerr(tf.grad.cpu().numpy(), 3.0 * o["dfeat"]) < TOL
+    kept = tf.grad.clone()
+    with pytest.raises(RuntimeError, match="already consumed"):
+        (2.0 * err).backward()
+    assert torch.equal(tf.grad, kept)                                # the refused call left the first result untouched
+
+    tf, tv, ts, tb = leaves()
+    err, _ = av.synth_masks_loss(tf, tv, ts, tb, [_cuda(t) for t in gts], _cuda(wgt), loss="bce", fused=False)
+    (3.0 * err).backward(retain_graph=True)
+    assert relerr(tf.grad.cpu().numpy(), 3.0 * o["dfeat"]) < TOL
+    (2.0 * err).backward()                                           # accumulates 3 g + 2 g
+    assert relerr(tf.grad.cpu().numpy(), 5.0 * o["dfeat"]) < TOL
+    assert relerr(tv.grad.cpu().numpy(), 5.0 * o["dvecs"]) < TOL
+    assert relerr(ts.grad.cpu().numpy(), 5.0 * o["dscale"]) < TOL
+    assert abs(float(tb.grad) - 5.0 * o["dbias"]) / abs(5.0 * o["dbias"]) < TOL
+
+
 def test_bce_saturation_semantics_on_gpu(golden):
     """z = +-40 etc.: loss term 100 * w, gradient exactly zero where sigmoid saturates."""
     g = golden("synth")

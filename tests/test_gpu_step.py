@@ -270,7 +270,8 @@ def test_long_clip_windows_vs_oracle():
 
     out = av.separate_long_clip(torch.from_numpy(src).cuda(), mask_fn, binary_mask=False)
     assert seen["shape"] == (3, 1, 256, 256) and out.shape == (3, 3, 65280)
-    wins = av.clip_windows(torch.from_numpy(src), 65535, 65535).numpy()
+    wins = av.clip_windows(torch.from_numpy(src)).numpy()          # default stride 65280: seamless tiling
+    assert wins.shape[0] == 3
     for i in range(3):
         amp, ph = O.stft_magphase(wins[i])
         mix_o, pred_o, _ = O.separate(amp[None, None], ph[None, None], [masks_np[n][i][None, None] for n in range(2)], binary_mask=False)
@@ -278,8 +279,11 @@ def test_long_clip_windows_vs_oracle():
         got = out[i].cpu().numpy()
         assert np.max(np.abs(got[0] - mix_o[0])) / s < TOL
         assert np.max(np.abs(got[1:] - pred_o[0])) / s < TOL
-    full = av.assemble_windows(out[:, 0], 65535, L_long).cpu().numpy()
-    assert np.max(np.abs(full[:65280] - src[:65280])) < 1e-4
+    # the mixture channel round-trips over the WHOLE clip (no zero gaps at the window boundaries); only the last
+    # samples of the clip, beyond what the zero-padded tail window reconstructs, are outside the check
+    full = av.assemble_windows(out[:, 0], 65280, L_long).cpu().numpy()
+    covered = min(L_long, 2 * 65280 + 65280)
+    assert np.max(np.abs(full[:covered] - src[:covered])) < 1e-4
 
 
 def test_full_size_c3_and_c5_properties():
