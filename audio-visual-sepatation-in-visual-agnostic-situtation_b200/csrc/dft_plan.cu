@@ -499,8 +499,9 @@ static int launch_ifold(avsep_plan* pl, int S, float* wav_dev, cudaStream_t stre
   ip.err_flag = pl->err_flag;
   const int grid2 = 2 * std::min(2 * S, sm_count() / 2);
   if (grid2 <= 0) return AVSEP_OK;
-  AVSEP_CUDA(cudaFuncSetAttribute(idft_fold2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IFoldCfg::SMEM_BYTES));
-  idft_fold2_kernel<<<grid2, IFOLD_THREADS, IFoldCfg::SMEM_BYTES, stream>>>(pl->tm_basis_ifold, pl->tm_spec_ifold, ip);
+  auto kern = idft_fold2_kernel<IFoldCfg::BK>;
+  AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IFoldCfg::SMEM_BYTES));
+  kern<<<grid2, IFOLD_THREADS, IFoldCfg::SMEM_BYTES, stream>>>(pl->tm_basis_ifold, pl->tm_spec_ifold, ip);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
