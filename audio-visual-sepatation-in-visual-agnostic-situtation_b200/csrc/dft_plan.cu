@@ -139,10 +139,18 @@ __global__ void wave_frames_kernel(const float* __restrict__ wave, int S, int L,
   }
 }
 
-// K4 front half (main.py:213-246): un-warp each predicted mask to the linear frequency axis,
-// threshold, multiply the mixture spectrum and emit the inverse-DFT operand X[t, k] = (re | im),
-// time-major, as bf16 hi/lo.  One CTA = 64 bins x 32 frames of one mixture; the spectrum tile is
-// transposed through shared memory so both the [f][t] reads and the [t][f] writes are coalesced.
+// K4 front half (main.py:213-246): un-warp each predicted mask to the linear frequency axis, threshold, multiply
+// the mixture spectrum and emit the inverse-DFT operand X[t, k] = (re | im), time-major, as bf16 hi/lo.
+// HBM-bound streaming kernels, no shared-memory transpose.
+// spec_prep_vec_kernel (T even): a thread owns a register tile of 2 CONSECUTIVE frames x 8 CONSECUTIVE bins.
+//   * reads  [f][t]: one 64-bit load per bin row; a warp (16 frame pairs x 2 bin groups) reads 128-byte runs
+//   * writes [t][f]: the 8 bins of one frame are one 128-bit store per (re | im, hi | lo) plane; the 2 bin groups of a
+//     warp and the 4 warps of a CTA fill 128 contiguous bytes of every operand row
+//   * the mixture (re, im) tile is loaded once and reused by all N + 1 signals
+//   * consecutive bins share un-warp rows: the x-interpolated values (4 frames) of the two most recent mask rows stay
+//     in registers (about 1.3 mask row fetches per bin instead of 4 taps per element);
+//     small tile = few registers = many resident warps: the kernel lives on memory-level parallelism
+// spec_prep_scalar_kernel: one frame x 16 bins per thread, any T (ragged clips).
 struct SpecPrepParams {
   const float* masks;   // [N, B, Hm, T]
   const float* mag;     // [B, 512, T]
@@ -159,34 +167,60 @@ struct SpecPrepParams {
   size_t lo_stride;
 };
 
-constexpr int SPEC_PITCH = 68;      // floats per time row of the transpose tile: 64 bins + 4 (keeps rows 16-byte aligned)
+constexpr int SPEC_BINS_PER_THREAD = 16;
+constexpr int SPEC_FRAMES_PER_CTA = 16;
+constexpr int SPEC_BINS_PER_CTA = 256;            // 8 warps x 2 bin groups x 16 bins
 
-__global__ void __launch_bounds__(256) spec_prep_kernel(const SpecPrepParams p) {
-  __shared__ __align__(16) float tile[2][32][SPEC_PITCH];
-  const int b = blockIdx.z;
-  const int f0 = blockIdx.y * 64;
-  const int t0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31;
-  const int ty = threadIdx.x >> 5;
-  const int t = t0 + tx;
-  const bool t_ok = t < p.T;
-  // a thread owns 8 CONSECUTIVE bins of one frame: consecutive bins share un-warp rows, so the x-interpolated value
-  // of the two most recent mask rows is kept in registers (4x fewer mask loads than a 4-tap gather per element)
-  const int fb = f0 + ty * 8;
-  float bre[8], bim[8];
+// 16 fp32 values -> bf16 hi / lo (x ~= hi + lo), two 128-bit stores each
+__device__ __forceinline__ void spec_store16(const float (&v)[SPEC_BINS_PER_THREAD], __nv_bfloat16* __restrict__ hi_dst,
+                                             __nv_bfloat16* __restrict__ lo_dst) {
+  uint32_t h[8], l[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    bre[i] = 0.f;
-    bim[i] = 0.f;
-    if (t_ok) {
-      const size_t o = ((size_t)b * AVSEP_N_BINS + fb + i) * p.T + t;
-      if (p.re) {
-        bre[i] = __ldg(p.re + o);
-        bim[i] = __ldg(p.im + o);
-      } else {
-        const float mg = __ldg(p.mag + o);
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  uint4* hd = reinterpret_cast<uint4*>(hi_dst);
+  uint4* ld = reinterpret_cast<uint4*>(lo_dst);
+  hd[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  hd[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  ld[0] = make_uint4(l[0], l[1], l[2], l[3]);
+  ld[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+__global__ void __launch_bounds__(256) spec_prep_scalar_kernel(const SpecPrepParams p) {
+  __shared__ int s_y0[SPEC_BINS_PER_CTA];
+  __shared__ float s_fy[SPEC_BINS_PER_CTA];
+  const int b = blockIdx.z;
+  const int f_cta = blockIdx.y * SPEC_BINS_PER_CTA;
+  const int t = blockIdx.x * SPEC_FRAMES_PER_CTA + (threadIdx.x & 15);
+  const int grp = threadIdx.x >> 4;               // 0..15: bin group inside the CTA
+  const int fb = f_cta + grp * SPEC_BINS_PER_THREAD;
+  if (p.log_freq && p.N > 0) {
+    s_y0[threadIdx.x] = __ldg(p.ytap.i0 + f_cta + threadIdx.x);
+    s_fy[threadIdx.x] = __ldg(p.ytap.frac + f_cta + threadIdx.x);
+    __syncthreads();
+  }
+  if (t >= p.T) return;
+  // mixture spectrum of the thread's bins (shared by all signals)
+  float bre[SPEC_BINS_PER_THREAD], bim[SPEC_BINS_PER_THREAD];
+  {
+    const size_t o = ((size_t)b * AVSEP_N_BINS + fb) * p.T + t;
+    if (p.re) {
+#pragma unroll
+      for (int i = 0; i < SPEC_BINS_PER_THREAD; ++i) {
+        bre[i] = __ldg(p.re + o + (size_t)i * p.T);
+        bim[i] = __ldg(p.im + o + (size_t)i * p.T);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < SPEC_BINS_PER_THREAD; ++i) {
+        const float mg = __ldg(p.mag + o + (size_t)i * p.T);
         float sn, cs;
-        sincosf(__ldg(p.phase + o), &sn, &cs);
+        sincosf(__ldg(p.phase + o + (size_t)i * p.T), &sn, &cs);
         bre[i] = mg * cs;
         bim[i] = mg * sn;
       }
@@ -194,63 +228,196 @@ __global__ void __launch_bounds__(256) spec_prep_kernel(const SpecPrepParams p) 
   }
   int x0 = 0;
   float fx = 0.f;
-  if (t_ok && p.log_freq) {
+  if (p.log_freq) {
     x0 = __ldg(p.xtap.i0 + t);
     fx = __ldg(p.xtap.frac + t);
   }
   const bool xa = x0 >= 0, xb = x0 + 1 < p.T;
+  const float wa = xa ? 1.f - fx : 0.f, wb = xb ? fx : 0.f;
+  const int xa_i = xa ? x0 : 0, xb_i = xb ? x0 + 1 : 0;
   const int nsig = p.N + p.include_mix;
-  for (int j = 0; j < nsig; ++j) {
-    const int n = j - p.include_mix;   // -1 = mixture (mask 1)
-    const float* mp = n >= 0 ? p.masks + ((size_t)n * p.B + b) * (size_t)p.Hm * p.T : nullptr;
-    int cy0 = -2, cy1 = -2;
-    float cv0 = 0.f, cv1 = 0.f;
-    auto row = [&](int y) -> float {                       // x-interpolated mask row y at this frame (0 outside)
-      if (y == cy0) return cv0;
-      if (y == cy1) return cv1;
-      if (y < 0 || y >= p.Hm) return 0.f;
-      const float* r = mp + (size_t)y * p.T;
-      return (xa ? (1.f - fx) * __ldg(r + x0) : 0.f) + (xb ? fx * __ldg(r + x0 + 1) : 0.f);
-    };
+  for (int jsig = 0; jsig < nsig; ++jsig) {
+    const int n = jsig - p.include_mix;            // -1 = mixture (mask 1)
+    float vre[SPEC_BINS_PER_THREAD], vim[SPEC_BINS_PER_THREAD];
+    if (n < 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float mk = 1.f;
-      if (n >= 0 && t_ok) {
-        if (p.log_freq) {
-          const int y0 = __ldg(p.ytap.i0 + fb + i);
-          const float fy = __ldg(p.ytap.frac + fb + i);
+      for (int i = 0; i < SPEC_BINS_PER_THREAD; ++i) { vre[i] = bre[i]; vim[i] = bim[i]; }
+    } else {
+      const float* mp = p.masks + ((size_t)n * p.B + b) * (size_t)p.Hm * p.T;
+      if (p.log_freq) {
+        int cy0 = -2, cy1 = -2;
+        float cv0 = 0.f, cv1 = 0.f;
+        auto row = [&](int y) -> float {           // x-interpolated mask row y at this frame (0 outside the image)
+          if (y == cy0) return cv0;
+          if (y == cy1) return cv1;
+          if (y < 0 || y >= p.Hm) return 0.f;
+          const float* r = mp + (size_t)y * p.T;
+          return wa * __ldg(r + xa_i) + wb * __ldg(r + xb_i);
+        };
+#pragma unroll
+        for (int i = 0; i < SPEC_BINS_PER_THREAD; ++i) {
+          const int y0 = s_y0[grp * SPEC_BINS_PER_THREAD + i];
+          const float fy = s_fy[grp * SPEC_BINS_PER_THREAD + i];
           const float r0 = row(y0), r1 = row(y0 + 1);
           cy0 = y0; cv0 = r0; cy1 = y0 + 1; cv1 = r1;
-          mk = (1.f - fy) * r0 + fy * r1;
-        } else {
-          mk = __ldg(mp + (size_t)(fb + i) * p.T + t);
+          float mk = (1.f - fy) * r0 + fy * r1;
+          if (p.binary) mk = mk > p.thres ? 1.f : 0.f;
+          vre[i] = bre[i] * mk;
+          vim[i] = bim[i] * mk;
         }
-        if (p.binary) mk = mk > p.thres ? 1.f : 0.f;
-      }
-      tile[0][tx][ty * 8 + i] = bre[i] * mk;
-      tile[1][tx][ty * 8 + i] = bim[i] * mk;
-    }
-    __syncthreads();
-    // write 32 time rows x (64 re + 64 im) x (hi, lo): one 128-bit shared load -> two 8-byte stores (4 bf16) per item
-    const size_t sig = (size_t)b * nsig + j;
-    for (int c = threadIdx.x; c < 32 * 2 * 16; c += 256) {
-      const int tr = c >> 5;            // time row in tile
-      const int part = (c >> 4) & 1;    // 0 re, 1 im
-      const int g = c & 15;             // group of 4 bins
-      if (t0 + tr < p.T) {
-        const float4 v = *reinterpret_cast<const float4*>(&tile[part][tr][g * 4]);
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-        const float2 f0h = __bfloat1622float2(h0), f1h = __bfloat1622float2(h1);
-        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0h.x, v.y - f0h.y), l1 = __floats2bfloat162_rn(v.z - f1h.x, v.w - f1h.y);
-        const size_t o = (sig * p.T + (t0 + tr)) * DFT_K + part * AVSEP_N_BINS + f0 + g * 4;
-        uint2 hv, lv;
-        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
-        *reinterpret_cast<uint2*>(p.out + o) = hv;
-        *reinterpret_cast<uint2*>(p.out + p.lo_stride + o) = lv;
+      } else {
+#pragma unroll
+        for (int i = 0; i < SPEC_BINS_PER_THREAD; ++i) {
+          float mk = __ldg(mp + (size_t)(fb + i) * p.T + t);
+          if (p.binary) mk = mk > p.thres ? 1.f : 0.f;
+          vre[i] = bre[i] * mk;
+          vim[i] = bim[i] * mk;
+        }
       }
     }
+    const size_t sig = (size_t)b * nsig + jsig;
+    __nv_bfloat16* orow = p.out + (sig * p.T + t) * DFT_K + fb;
+    spec_store16(vre, orow, orow + p.lo_stride);
+    spec_store16(vim, orow + AVSEP_N_BINS, orow + p.lo_stride + AVSEP_N_BINS);
+  }
+}
+
+constexpr int SPECV_FRAMES = 2, SPECV_BINS = 8;
+constexpr int SPECV_THREADS = 128;
+constexpr int SPECV_FRAMES_PER_CTA = 32;          // 16 frame pairs per warp
+constexpr int SPECV_BINS_PER_CTA = 64;            // 4 warps x 2 bin groups x 8 bins
+
+// 8 fp32 values -> bf16 hi / lo (x ~= hi + lo), one 128-bit store each
+__device__ __forceinline__ void spec_store8(const float (&v)[SPECV_BINS], __nv_bfloat16* __restrict__ hi_dst,
+                                            __nv_bfloat16* __restrict__ lo_dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(SPECV_THREADS, 6) spec_prep_vec_kernel(const SpecPrepParams p) {
+  __shared__ int s_y0[SPECV_BINS_PER_CTA];
+  __shared__ float s_fy[SPECV_BINS_PER_CTA];
+  const int b = blockIdx.z;
+  const int f_cta = blockIdx.y * SPECV_BINS_PER_CTA;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * SPECV_FRAMES_PER_CTA + (lane & 15) * SPECV_FRAMES;      // first of this thread's 2 frames
+  const int grp = warp * 2 + (lane >> 4);                                            // 0..7: bin group inside the CTA
+  const int fb = f_cta + grp * SPECV_BINS;
+  if (p.log_freq && p.N > 0) {
+    if (threadIdx.x < SPECV_BINS_PER_CTA) {
+      s_y0[threadIdx.x] = __ldg(p.ytap.i0 + f_cta + threadIdx.x);
+      s_fy[threadIdx.x] = __ldg(p.ytap.frac + f_cta + threadIdx.x);
+    }
     __syncthreads();
+  }
+  if (t0 >= p.T) return;                           // T % 2 == 0: a frame pair is inside the clip or outside it
+  // mixture spectrum tile (shared by all signals): [bin][frame]
+  float bre[SPECV_BINS][SPECV_FRAMES], bim[SPECV_BINS][SPECV_FRAMES];
+  {
+    const size_t o = ((size_t)b * AVSEP_N_BINS + fb) * p.T + t0;
+#pragma unroll
+    for (int i = 0; i < SPECV_BINS; ++i) {
+      if (p.re) {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(p.re + o + (size_t)i * p.T));
+        const float2 m = __ldg(reinterpret_cast<const float2*>(p.im + o + (size_t)i * p.T));
+        bre[i][0] = r.x; bre[i][1] = r.y;
+        bim[i][0] = m.x; bim[i][1] = m.y;
+      } else {
+        const float2 mg = __ldg(reinterpret_cast<const float2*>(p.mag + o + (size_t)i * p.T));
+        const float2 ph = __ldg(reinterpret_cast<const float2*>(p.phase + o + (size_t)i * p.T));
+        float sn, cs;
+        sincosf(ph.x, &sn, &cs);
+        bre[i][0] = mg.x * cs; bim[i][0] = mg.x * sn;
+        sincosf(ph.y, &sn, &cs);
+        bre[i][1] = mg.y * cs; bim[i][1] = mg.y * sn;
+      }
+    }
+  }
+  // x taps of the 2 frames: tap 0 is column t - 1 or t by construction of the linear grid (sel = 0 / 1)
+  int sel[SPECV_FRAMES] = {0, 0};
+  float fx[SPECV_FRAMES] = {0.f, 0.f};
+  if (p.log_freq) {
+    const int2 xi = __ldg(reinterpret_cast<const int2*>(p.xtap.i0 + t0));
+    const float2 xf = __ldg(reinterpret_cast<const float2*>(p.xtap.frac + t0));
+    sel[0] = xi.x - (t0 - 1); sel[1] = xi.y - t0;
+    fx[0] = xf.x; fx[1] = xf.y;
+  }
+  const int nsig = p.N + p.include_mix;
+  for (int jsig = 0; jsig < nsig; ++jsig) {
+    const int n = jsig - p.include_mix;            // -1 = mixture (mask 1)
+    const size_t sig = (size_t)b * nsig + jsig;
+    __nv_bfloat16* orow = p.out + (sig * p.T + t0) * DFT_K + fb;
+    float mk[SPECV_BINS][SPECV_FRAMES];
+    if (n < 0) {
+#pragma unroll
+      for (int i = 0; i < SPECV_BINS; ++i) { mk[i][0] = 1.f; mk[i][1] = 1.f; }
+    } else {
+      const float* mp = p.masks + ((size_t)n * p.B + b) * (size_t)p.Hm * p.T;
+      if (p.log_freq) {
+        int cy0 = -2, cy1 = -2;
+        float cv0[SPECV_FRAMES] = {0.f, 0.f}, cv1[SPECV_FRAMES] = {0.f, 0.f};
+        // x-interpolated mask row y at the 2 frames (0 outside the image): one 64-bit load + the two neighbours
+        auto row = [&](int y, float (&r)[SPECV_FRAMES]) {
+          if (y == cy0) { r[0] = cv0[0]; r[1] = cv0[1]; return; }
+          if (y == cy1) { r[0] = cv1[0]; r[1] = cv1[1]; return; }
+          if (y < 0 || y >= p.Hm) { r[0] = 0.f; r[1] = 0.f; return; }
+          const float* q = mp + (size_t)y * p.T + t0;
+          const float2 c = __ldg(reinterpret_cast<const float2*>(q));
+          float v[4];
+          v[0] = t0 > 0 ? __ldg(q - 1) : 0.f;
+          v[1] = c.x; v[2] = c.y;
+          v[3] = t0 + 2 < p.T ? __ldg(q + 2) : 0.f;
+#pragma unroll
+          for (int e = 0; e < SPECV_FRAMES; ++e) {
+            const float a = sel[e] ? v[e + 1] : v[e];        // tap x0 (x0 = t - 1 + sel)
+            const float c2 = sel[e] ? v[e + 2] : v[e + 1];   // tap x0 + 1
+            r[e] = (1.f - fx[e]) * a + fx[e] * c2;           // out-of-image taps contribute 0
+          }
+        };
+#pragma unroll
+        for (int i = 0; i < SPECV_BINS; ++i) {
+          const int y0 = s_y0[grp * SPECV_BINS + i];
+          const float fy = s_fy[grp * SPECV_BINS + i];
+          float r0[SPECV_FRAMES], r1[SPECV_FRAMES];
+          row(y0, r0);
+          row(y0 + 1, r1);
+          cy0 = y0; cy1 = y0 + 1;
+#pragma unroll
+          for (int e = 0; e < SPECV_FRAMES; ++e) {
+            cv0[e] = r0[e]; cv1[e] = r1[e];
+            const float m = (1.f - fy) * r0[e] + fy * r1[e];
+            mk[i][e] = p.binary ? (m > p.thres ? 1.f : 0.f) : m;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < SPECV_BINS; ++i) {
+          const float2 c = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(fb + i) * p.T + t0));
+          mk[i][0] = p.binary ? (c.x > p.thres ? 1.f : 0.f) : c.x;
+          mk[i][1] = p.binary ? (c.y > p.thres ? 1.f : 0.f) : c.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < SPECV_FRAMES; ++e) {
+      float vre[SPECV_BINS], vim[SPECV_BINS];
+#pragma unroll
+      for (int i = 0; i < SPECV_BINS; ++i) {
+        vre[i] = n < 0 ? bre[i][e] : bre[i][e] * mk[i][e];
+        vim[i] = n < 0 ? bim[i][e] : bim[i][e] * mk[i][e];
+      }
+      spec_store8(vre, orow + (size_t)e * DFT_K, orow + (size_t)e * DFT_K + p.lo_stride);
+      spec_store8(vim, orow + (size_t)e * DFT_K + AVSEP_N_BINS, orow + (size_t)e * DFT_K + p.lo_stride + AVSEP_N_BINS);
+    }
   }
 }
 
@@ -964,8 +1131,13 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
   }
   sp.out = pl->spec_split;
   sp.lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
-  dim3 grid(ceil_div(pl->T, 32), AVSEP_N_BINS / 64, B);
-  spec_prep_kernel<<<grid, 256, 0, stream>>>(sp);
+  if ((pl->T & 1) == 0) {
+    dim3 grid(ceil_div(pl->T, SPECV_FRAMES_PER_CTA), AVSEP_N_BINS / SPECV_BINS_PER_CTA, B);
+    spec_prep_vec_kernel<<<grid, SPECV_THREADS, 0, stream>>>(sp);
+  } else {
+    dim3 grid(ceil_div(pl->T, SPEC_FRAMES_PER_CTA), AVSEP_N_BINS / SPEC_BINS_PER_CTA, B);
+    spec_prep_scalar_kernel<<<grid, 256, 0, stream>>>(sp);
+  }
   AVSEP_LAUNCH_CHECK();
   if (pl->inverse_fold) return launch_ifold(pl, B * nsig, wav_dev, stream);
   DftParams prm = base_params(pl, B * nsig);
