@@ -12,7 +12,7 @@ The directory name carries the upstream repo name (hyphens), so import it throug
 from . import _lib
 from ._lib import AvsepError, LIB_PATH
 from . import ops
-from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pit_loss, pit_lossmat, separate, stft, stft_mix,
+from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pcm16_to_wave, pit_loss, pit_lossmat, separate, stft, stft_mix,
                   synth_masks, synth_masks_loss, synth_nosum, synth_pixelwise)
 from . import modules
 from .modules import BCELoss, BaseLoss, Bias, InnerProd, L1Loss, L2Loss, PitWrapper, activate
@@ -26,7 +26,7 @@ from .bss_metrics import bss_eval_batch
 __all__ = [
     "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel", "bss_metrics", "bss_eval_batch",
     "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
-    "stft", "stft_mix", "istft", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
+    "stft", "stft_mix", "istft", "pcm16_to_wave", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
     "_stft", "_mix_n_and_stft", "stft_batch", "Step", "clip_windows", "assemble_windows", "separate_long_clip",
     "synth_masks", "synth_masks_loss", "synth_nosum", "synth_pixelwise", "list_loss", "pit_loss", "pit_lossmat",
     "InnerProd", "Bias", "BaseLoss", "BCELoss", "L1Loss", "L2Loss", "PitWrapper", "activate",

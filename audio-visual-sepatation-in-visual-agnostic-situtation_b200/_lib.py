@@ -67,6 +67,7 @@ SIGNATURES = {
     "avsep_plan_set_mix_linear": (_I, [_P, _I]),
     "avsep_stft_mix": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "avsep_stft": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "avsep_stft_reim": (_I, [_P, _P, _I, _P, _P, _P, _I, _P]),
     "avsep_separate": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P]),
     "avsep_istft": (_I, [_P, _P, _P, _I, _P, _P]),
     "avsep_debug_raw_gemm": (_I, [_P, _I, _I, _P, _P]),
@@ -94,6 +95,9 @@ SIGNATURES = {
     "avsep_step_train_host_async": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "avsep_step_train_dev": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "avsep_step_eval_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
+    "avsep_step_eval_host_async": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
+    "avsep_step_train_pcm16_async": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "avsep_pcm16_to_wave": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "avsep_step_eval_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "avsep_step_buffer": (_P, [_P, _I]),
     "avsep_step_plan": (_P, [_P]),

@@ -1082,6 +1082,12 @@ int avsep_stft(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, flo
   return stft_impl(pl, wave_dev, S, mag_dev, phase_dev, re_dev, im_dev, S, stream, 0, 0);
 }
 
+int avsep_stft_reim(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* re_dev, float* im_dev, int reim_count,
+                    void* stream) {
+  AVSEP_REQUIRE(reim_count >= 0 && reim_count <= S, "avsep_stft_reim: reim_count = %d outside [0, S = %d]", reim_count, S);
+  return stft_impl(pl, wave_dev, S, mag_dev, nullptr, re_dev, im_dev, reim_count, stream, 0, 0);
+}
+
 int avsep_stft_mix(avsep_plan* pl, const float* sources_dev, int B, int N, float* mag_dev, float* phase_dev, void* stream) {
   AVSEP_REQUIRE(B >= 0 && N >= 1 && N <= AVSEP_MAX_SRC, "avsep_stft_mix: bad B = %d / N = %d", B, N);
   return stft_impl(pl, sources_dev, (N + 1) * B, mag_dev, phase_dev, nullptr, nullptr, 0, stream, B, N);

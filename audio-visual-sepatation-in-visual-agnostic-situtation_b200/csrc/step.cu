@@ -4,6 +4,7 @@
 // Host-buffer variants add the H2D copy of the waveforms / K-vectors and the D2H copy of the result
 // inside the call.  feat_sound is the U-Net's output in the reference and never exists on the host
 // there, so it stays a device pointer.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -57,6 +58,8 @@ struct avsep_step {
   float* dscale = nullptr;    // [K]
   float* dbias = nullptr;     // [1]
   float* wav = nullptr;       // [B, N+1, out_len]
+  int16_t* pcm = nullptr;     // [N+1, B, L] 16-bit PCM staging of the opt-in hand-off (allocated on first use)
+  float* gains = nullptr;     // [N+1, B] per-clip amplitude gains of that hand-off
   void* scratch = nullptr;
 };
 
@@ -85,6 +88,48 @@ static int step_forward_common(avsep_step* st, const float* waves_dev, const flo
                             AVSEP_LOSS_BCE, st->gt, st->weights, st->loss, st->scratch, stream);
 }
 
+// 16-bit PCM hand-off (dataset/base.py:150-172 + dataset/music.py:120): the loader's float waveform is
+//   audio = int16 / 32768 (wav decode) ; audio *= gain (train-time augmentation, base.py:165-167) ; clip to [-1, 1] ; / num_mix
+// -- the same fp32 operations in the same order here, so the device waveform is bit-identical to the one the reference's
+// loader would have produced from the same PCM samples, at half the H2D bytes.
+__global__ void __launch_bounds__(256) pcm16_to_wave_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ gains,
+                                                            float* __restrict__ wave, int L, float num_mix) {
+  const int clip = blockIdx.y;
+  const float g = gains ? __ldg(gains + clip) : 1.0f;
+  const int16_t* src = pcm + (size_t)clip * L;
+  float* dst = wave + (size_t)clip * L;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    float x = (float)src[i] * (1.0f / 32768.0f);       // exact
+    x = x * g;                                         // numpy float32 multiply (round to nearest)
+    x = fminf(fmaxf(x, -1.0f), 1.0f);
+    dst[i] = __fdiv_rn(x, num_mix);                    // numpy float32 / int -> float32 division
+  }
+}
+
+// H2D copies of the PCM samples (and gains), enqueued back to back with the caller's other input copies; the conversion
+// kernel is launched by pcm16_convert AFTER all copies of the step (a kernel between two copies of a stream keeps the
+// next step's copy from overlapping this step's kernels)
+static int pcm16_copy(avsep_step* st, const int16_t* pcm_host, const float* gains_host, cudaStream_t stream) {
+  const int signals = st->N + (st->mix_on_device ? 0 : 1);
+  const size_t n = (size_t)signals * st->B * st->L;
+  if (!st->pcm) {
+    AVSEP_CUDA(cudaMalloc(&st->pcm, sizeof(int16_t) * (size_t)(st->N + 1) * st->B * st->L));
+    AVSEP_CUDA(cudaMalloc(&st->gains, sizeof(float) * (size_t)(st->N + 1) * st->B));
+  }
+  AVSEP_CUDA(cudaMemcpyAsync(st->pcm, pcm_host, sizeof(int16_t) * n, cudaMemcpyHostToDevice, stream));
+  if (gains_host)
+    AVSEP_CUDA(cudaMemcpyAsync(st->gains, gains_host, sizeof(float) * (size_t)signals * st->B, cudaMemcpyHostToDevice, stream));
+  return AVSEP_OK;
+}
+
+static int pcm16_convert(avsep_step* st, bool with_gains, cudaStream_t stream) {
+  const int signals = st->N + (st->mix_on_device ? 0 : 1);
+  dim3 grid(std::min(ceil_div(st->L, 256 * 8), 64), signals * st->B);
+  pcm16_to_wave_kernel<<<grid, 256, 0, stream>>>(st->pcm, with_gains ? st->gains : nullptr, st->waves, st->L, (float)st->N);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
 extern "C" {
 
 int avsep_step_destroy(avsep_step* st) {
@@ -95,6 +140,8 @@ int avsep_step_destroy(avsep_step* st) {
                    st->gt, st->pred, st->loss, st->one, st->dvecs, st->dscale, st->dbias, st->wav};
   for (float* b : bufs) cudaFree(b);
   cudaFree(st->scratch);
+  cudaFree(st->pcm);
+  cudaFree(st->gains);
   delete st;
   return AVSEP_OK;
 }
@@ -234,6 +281,36 @@ int avsep_step_train_host_async(avsep_step* st, const float* waves_host, const f
   return AVSEP_OK;
 }
 
+int avsep_step_train_pcm16_async(avsep_step* st, const int16_t* pcm_host, const float* gains_host, const float* vecs_host,
+                                 const float* feat_dev, const float* scale_dev, const float* bias_dev, float* dfeat_dev,
+                                 float* dvecs_host, float* loss_host, void* stream_) {
+  AVSEP_REQUIRE(st && pcm_host && vecs_host && feat_dev && loss_host, "avsep_step_train_pcm16_async: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = pcm16_copy(st, pcm_host, gains_host, stream);
+  if (rc) return rc;
+  AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
+  rc = pcm16_convert(st, gains_host != nullptr, stream);
+  if (rc) return rc;
+  rc = avsep_step_train_dev(st, st->waves, st->vecs, feat_dev, scale_dev, bias_dev, dfeat_dev, nullptr, nullptr, nullptr,
+                            nullptr, stream);
+  if (rc) return rc;
+  AVSEP_CUDA(cudaMemcpyAsync(loss_host, st->loss, sizeof(float), cudaMemcpyDeviceToHost, stream));
+  if (dvecs_host)
+    AVSEP_CUDA(cudaMemcpyAsync(dvecs_host, st->dvecs, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyDeviceToHost, stream));
+  return AVSEP_OK;
+}
+
+int avsep_pcm16_to_wave(const int16_t* pcm_dev, const float* gains_dev, int clips, int L, int num_mix, float* wave_dev, void* stream) {
+  AVSEP_REQUIRE(pcm_dev && wave_dev && clips >= 0 && clips <= 65535 && L >= 1 && num_mix >= 1, "avsep_pcm16_to_wave: bad argument");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (clips == 0) return AVSEP_OK;
+  dim3 grid(std::min(ceil_div(L, 256 * 8), 64), clips);
+  pcm16_to_wave_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pcm_dev, gains_dev, wave_dev, L, (float)num_mix);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
 int avsep_step_train_host(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
                           const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_host, float* loss_host,
                           void* stream) {
@@ -252,6 +329,20 @@ int avsep_step_eval_dev(avsep_step* st, const float* waves_dev, const float* vec
   if (rc) return rc;
   return avsep_separate(st->plan, st->pred, st->N, st->B, nullptr, nullptr, st->mix_re, st->mix_im, 1, binary_mask, mask_thres, 1,
                         wav_dev ? wav_dev : st->wav, stream);
+}
+
+int avsep_step_eval_host_async(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,
+                               const float* scale_dev, const float* bias_dev, int binary_mask, float mask_thres, float* wav_host,
+                               void* stream_) {
+  AVSEP_REQUIRE(st && waves_host && vecs_host && feat_dev, "avsep_step_eval_host_async: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AVSEP_CUDA(cudaMemcpyAsync(st->waves, waves_host, sizeof(float) * (size_t)(st->N + (st->mix_on_device ? 0 : 1)) * st->B * st->L, cudaMemcpyHostToDevice, stream));
+  AVSEP_CUDA(cudaMemcpyAsync(st->vecs, vecs_host, sizeof(float) * (size_t)st->B * st->N * st->K, cudaMemcpyHostToDevice, stream));
+  int rc = avsep_step_eval_dev(st, st->waves, st->vecs, feat_dev, scale_dev, bias_dev, binary_mask, mask_thres, st->wav, stream);
+  if (rc) return rc;
+  if (wav_host)      // NULL: the separated waveforms stay on the device (avsep_step_buffer 13) for a device-side evaluator
+    AVSEP_CUDA(cudaMemcpyAsync(wav_host, st->wav, sizeof(float) * (size_t)st->B * (st->N + 1) * st->out_len, cudaMemcpyDeviceToHost, stream));
+  return AVSEP_OK;
 }
 
 int avsep_step_eval_host(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,

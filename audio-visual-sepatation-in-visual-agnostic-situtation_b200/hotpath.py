@@ -353,6 +353,34 @@ class Step:
                                               ops._p(bias), ops._p(dfeat), ops._p(dvecs_host), loss_host.data_ptr(), ops._stream()),
               "avsep_step_train_host_async")
 
+    def train_pcm16_async(self, pcm_host, gains_host, vecs_host, feat, scale, bias, dfeat, loss_host, dvecs_host=None):
+        """Opt-in 16-bit PCM hand-off: pcm_host int16 [N+1,B,L] (or [N,B,L] sources only) pinned, gains_host float32
+        [signals,B] or None; the loader's int16/32768 -> *gain -> clip -> /N runs on the device (dataset/base.py:156-172,
+        dataset/music.py:120), bit-identical to the float32 hand-off at half the H2D bytes."""
+        signals = self.N if getattr(self, "mix_on_device", False) else self.N + 1
+        if pcm_host.dtype != torch.int16 or pcm_host.numel() != signals * self.B * self.L or not pcm_host.is_contiguous():
+            raise _lib.AvsepError(f"Step.train_pcm16_async: pcm must be contiguous int16 [{signals}, {self.B}, {self.L}], "
+                                  f"got {tuple(pcm_host.shape)} {pcm_host.dtype}")
+        if gains_host is not None and (gains_host.dtype != torch.float32 or gains_host.numel() != signals * self.B):
+            raise _lib.AvsepError(f"Step.train_pcm16_async: gains must be float32 [{signals}, {self.B}]")
+        check(lib.avsep_step_train_pcm16_async(self._h, pcm_host.data_ptr(), ops._p(gains_host), vecs_host.data_ptr(), feat.data_ptr(),
+                                               ops._p(scale), ops._p(bias), ops._p(dfeat), ops._p(dvecs_host), loss_host.data_ptr(),
+                                               ops._stream()), "avsep_step_train_pcm16_async")
+
+    def eval_host_async(self, waves_host, vecs_host, feat, scale, bias, wav_host=None, binary_mask=True, mask_thres=0.5):
+        """Enqueue H2D + eval step (+ D2H of the waveforms when wav_host is given) on the current stream and return."""
+        self._check_waves(waves_host, "Step.eval_host_async")
+        check(lib.avsep_step_eval_host_async(self._h, waves_host.data_ptr(), vecs_host.data_ptr(), feat.data_ptr(), ops._p(scale),
+                                             ops._p(bias), int(binary_mask), float(mask_thres), ops._p(wav_host), ops._stream()),
+              "avsep_step_eval_host_async")
+
+    def view(self, name: str) -> torch.Tensor:
+        """Borrowed (no copy) view of one of the step's device buffers; valid until the step is closed."""
+        ptr = lib.avsep_step_buffer(self._h, self.BUFFERS[name])
+        if not ptr:
+            raise _lib.AvsepError(f"Step.view: no buffer named {name}")
+        return torch.as_tensor(_DevView(int(ptr), self._shape(name)), device="cuda")
+
     def eval_dev(self, waves, vecs, feat, scale, bias, wav=None, binary_mask=True, mask_thres=0.5):
         self._check_waves(waves, "Step.eval_dev")
         check(lib.avsep_step_eval_dev(self._h, waves.data_ptr(), vecs.data_ptr(), feat.data_ptr(), ops._p(scale), ops._p(bias),

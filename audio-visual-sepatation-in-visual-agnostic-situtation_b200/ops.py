@@ -189,6 +189,24 @@ def stft_mix(sources: torch.Tensor, *, phase: bool = False, plan: Optional[Plan]
     return mag.view(shape), (ph.view(shape) if ph is not None else None)
 
 
+def pcm16_to_wave(pcm: torch.Tensor, gains: Optional[torch.Tensor] = None, num_mix: int = 1) -> torch.Tensor:
+    """The loader's float path on the device: int16 [..., L] -> float32 = clip(int16 / 32768 * gain, -1, 1) / num_mix
+    (dataset/base.py:156-172, dataset/music.py:120), bit-identical to numpy's float32 arithmetic."""
+    if not pcm.is_cuda or pcm.dtype != torch.int16:
+        raise _lib.AvsepError(f"pcm16_to_wave: expected a CUDA int16 tensor, got {pcm.dtype} on {pcm.device}")
+    p_ = pcm.contiguous()
+    L = p_.shape[-1]
+    clips = p_.numel() // L if L else 0
+    g = None
+    if gains is not None:
+        g = _cuda_f32(gains, "pcm16_to_wave: gains")
+        if g.numel() != clips:
+            raise _lib.AvsepError(f"pcm16_to_wave: {g.numel()} gains for {clips} clips")
+    out = torch.empty(p_.shape, device=p_.device, dtype=torch.float32)
+    check(lib.avsep_pcm16_to_wave(p_.data_ptr(), _p(g), clips, L, int(num_mix), out.data_ptr(), _stream()), "avsep_pcm16_to_wave")
+    return out
+
+
 def istft(mag: torch.Tensor, phase: torch.Tensor, *, plan: Optional[Plan] = None) -> torch.Tensor:
     """utils.istft_reconstruction (utils.py:101-104), batched: [S,512,T] x2 -> [S, 256 (T-1)] float32 in [-1, 1]."""
     m = _cuda_f32(mag, "istft: mag")

@@ -78,6 +78,12 @@ size_t avsep_plan_workspace_bytes(const avsep_plan* plan);
 int avsep_stft(avsep_plan* plan, const float* wave_dev, int S,
                float* mag_dev, float* phase_dev, float* re_dev, float* im_dev, void* stream);
 
+/* Same transform, magnitudes of all S signals but (re, im) of the first reim_count signals only: re_dev / im_dev
+ * [reim_count, 512, T].  This is the eval step's forward transform (signal-major waves: the first B signals are the
+ * mixtures, whose complex spectrum the inverse transform needs; the sources only need |.| for the masks' targets). */
+int avsep_stft_reim(avsep_plan* plan, const float* wave_dev, int S, float* mag_dev, float* re_dev, float* im_dev,
+                    int reim_count, void* stream);
+
 /* STFT of B mixtures given only their N sources (the hand-off of dataset/music.py:120-127, where the mixture IS the
  * sum of the sources): sources_dev [N, B, L] -> mag_dev [(N+1) B, 512, T] with the mixtures in planes [0, B) and source
  * n in planes [(1+n) B, (2+n) B); phase_dev (same layout) is optional.  The mixture waveform is never materialised:
@@ -259,6 +265,20 @@ int avsep_step_train_host(avsep_step* step, const float* waves_host, const float
 int avsep_step_train_host_async(avsep_step* step, const float* waves_host, const float* vecs_host,
                                 const float* feat_dev, const float* scale_dev, const float* bias_dev,
                                 float* dfeat_dev, float* dvecs_host, float* loss_host, void* stream);
+/* Opt-in 16-bit PCM hand-off for the same step: the host passes the clips as the int16 samples the wav files hold,
+ * pcm_host [N+1, B, wave_len] (or [N, B, wave_len] with mix_on_device), plus optional per-clip gains gains_host
+ * [N+1, B] (NULL = 1.0; the train-time amplitude augmentation of dataset/base.py:165-167).  The device applies the
+ * loader's float32 operations in the loader's order -- x = int16 / 32768; x *= gain; clip to [-1, 1]; x /= N
+ * (dataset/base.py:156-172, dataset/music.py:120) -- so the waveform the STFT sees is bit-identical to the float32 one
+ * the reference's loader produces from the same samples, at half the H2D bytes.  Enqueue only, like
+ * avsep_step_train_host_async. */
+int avsep_step_train_pcm16_async(avsep_step* step, const int16_t* pcm_host, const float* gains_host,
+                                 const float* vecs_host, const float* feat_dev, const float* scale_dev,
+                                 const float* bias_dev, float* dfeat_dev, float* dvecs_host, float* loss_host,
+                                 void* stream);
+/* the conversion alone on device buffers: pcm_dev [clips, L] int16 (+ gains_dev [clips] or NULL) -> wave_dev [clips, L] */
+int avsep_pcm16_to_wave(const int16_t* pcm_dev, const float* gains_dev, int clips, int L, int num_mix,
+                        float* wave_dev, void* stream);
 /* same step with device-resident inputs, asynchronous (what bench.py's `value` times) */
 int avsep_step_train_dev(avsep_step* step, const float* waves_dev, const float* vecs_dev,
                          const float* feat_dev, const float* scale_dev, const float* bias_dev,
@@ -269,6 +289,11 @@ int avsep_step_train_dev(avsep_step* step, const float* waves_dev, const float* 
 int avsep_step_eval_host(avsep_step* step, const float* waves_host, const float* vecs_host,
                          const float* feat_dev, const float* scale_dev, const float* bias_dev,
                          int binary_mask, float mask_thres, float* wav_host, void* stream);
+/* eval_host without the final synchronisation (two steps on two streams overlap copies and kernels); wav_host may be
+ * NULL: the separated waveforms then stay on the device (avsep_step_buffer id 13) for a device-side evaluator. */
+int avsep_step_eval_host_async(avsep_step* step, const float* waves_host, const float* vecs_host,
+                               const float* feat_dev, const float* scale_dev, const float* bias_dev,
+                               int binary_mask, float mask_thres, float* wav_host, void* stream);
 int avsep_step_eval_dev(avsep_step* step, const float* waves_dev, const float* vecs_dev,
                         const float* feat_dev, const float* scale_dev, const float* bias_dev,
                         int binary_mask, float mask_thres, float* wav_dev, void* stream);

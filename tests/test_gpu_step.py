@@ -143,6 +143,73 @@ def test_train_step_vs_oracle():
     st.close()
 
 
+def test_pcm16_handoff_is_bit_identical_to_the_float_handoff():
+    """Opt-in 16-bit PCM hand-off (dataset/base.py:156-172, dataset/music.py:120): int16 / 32768 -> * gain -> clip -> / N on
+    the device, in the loader's fp32 order, equals numpy's float32 result bit for bit, and the train step fed with PCM
+    equals the step fed with that float waveform bit for bit."""
+    B, N, K = 2, 2, 32
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32768, size=(N, B, L), dtype=np.int16)
+    pcm[0, 0, :100] = 32767                                          # exercise the clip after the gain
+    pcm[1, 1, :100] = -32768
+    gains = (rng.random((N, B)) + 0.5).astype(np.float32)            # base.py:165-167: random.random() + 0.5
+    # the loader's arithmetic in numpy float32
+    audio = pcm.astype(np.float32) / np.float32(32768.0)
+    audio = audio * gains[:, :, None]
+    audio[audio > 1.] = 1.
+    audio[audio < -1.] = -1.
+    audio = (audio / N).astype(np.float32)
+    got = av.pcm16_to_wave(torch.from_numpy(pcm).cuda(), torch.from_numpy(gains).cuda(), num_mix=N).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, audio)
+    assert np.array_equal(av.pcm16_to_wave(torch.from_numpy(pcm).cuda(), None, num_mix=3).cpu().numpy(),
+                          (np.clip(pcm.astype(np.float32) / np.float32(32768.0), -1, 1) / 3).astype(np.float32))
+    # the whole train step: PCM in vs the float waveform in
+    _, feat, vecs, scale, bias = _inputs(B, N, K, seed=77)
+    c = lambda a: torch.from_numpy(a).cuda()
+    tfeat, tscale, tbias = c(feat), c(scale), c(bias)
+    vecs_host = torch.from_numpy(vecs).pin_memory()
+    res = {}
+    for mode in ("pcm16", "float"):
+        st = av.Step(B, N, K, L)
+        st.set_mix_on_device(True)
+        dfeat = torch.empty((B, K, 256, 256), device="cuda")
+        loss_host = torch.zeros(1).pin_memory()
+        dvecs_host = torch.empty((B, N, K)).pin_memory()
+        if mode == "pcm16":
+            st.train_pcm16_async(torch.from_numpy(pcm).pin_memory(), torch.from_numpy(gains).pin_memory(), vecs_host, tfeat, tscale, tbias,
+                                 dfeat, loss_host, dvecs_host)
+        else:
+            st.train_host_async(torch.from_numpy(audio).pin_memory(), vecs_host, tfeat, tscale, tbias, dfeat, loss_host, dvecs_host)
+        torch.cuda.synchronize()
+        res[mode] = (float(loss_host[0]), st.buffer("mag").clone(), dfeat.clone(), dvecs_host.clone())
+        st.close()
+    assert res["pcm16"][0] == res["float"][0] and res["float"][0] > 0
+    assert torch.equal(res["pcm16"][1], res["float"][1]) and torch.equal(res["pcm16"][2], res["float"][2])
+    assert torch.equal(res["pcm16"][3], res["float"][3])
+    st = av.Step(B, N, K, L)
+    with pytest.raises(av.AvsepError):                               # float buffer handed to the PCM entry point
+        st.train_pcm16_async(torch.zeros((N + 1, B, L)).pin_memory(), None, vecs_host, tfeat, tscale, tbias, None, torch.zeros(1).pin_memory())
+    st.close()
+
+
+def test_eval_host_async_equals_eval_dev():
+    """avsep_step_eval_host_async: host waveforms in, separated waveforms out (or left on the device), no sync inside."""
+    B, N, K = 2, 2, 32
+    waves, feat, vecs, scale, bias = _inputs(B, N, K, seed=5)
+    c = lambda a: torch.from_numpy(a).cuda()
+    st = av.Step(B, N, K, L)
+    wav_dev = torch.empty((B, N + 1, 65280), device="cuda")
+    st.eval_dev(c(waves), c(vecs), c(feat), c(scale), c(bias), wav_dev)
+    wav_host = torch.empty((B, N + 1, 65280)).pin_memory()
+    st.eval_host_async(torch.from_numpy(waves).pin_memory(), torch.from_numpy(vecs).pin_memory(), c(feat), c(scale), c(bias), wav_host)
+    torch.cuda.synchronize()
+    assert torch.equal(wav_host, wav_dev.cpu())
+    st.eval_host_async(torch.from_numpy(waves).pin_memory(), torch.from_numpy(vecs).pin_memory(), c(feat), c(scale), c(bias), None)
+    torch.cuda.synchronize()
+    assert torch.equal(st.view("wav"), wav_dev)
+    st.close()
+
+
 def test_step_rejects_wrong_waveform_layout():
     """The C-ABI takes raw pointers, so the Python wrapper checks that the waveform tensor matches the step's input
     layout ([N+1, B, L] with the mixture, or [N, B, L] sources after set_mix_on_device) instead of reading past its end."""
