@@ -157,7 +157,7 @@ __device__ __forceinline__ Row4 row_sample4(const float* __restrict__ base, int 
 }
 
 template <int NS>
-__global__ void __launch_bounds__(PREP_TX * PREP_TY, 4) prepare_vec_kernel(const PrepareParams p) {
+__global__ void __launch_bounds__(PREP_TX * PREP_TY, NS >= 3 ? 2 : 4) prepare_vec_kernel(const PrepareParams p) {
   const int b = blockIdx.z;
   const int h0 = (blockIdx.y * PREP_TY + threadIdx.y) * PREP_ROWS_PER_THREAD;
   if (h0 >= p.Hout) return;
