@@ -21,10 +21,10 @@ from .hotpath import (Step, _mix_n_and_stft, _stft, assemble_windows, calc_metri
                       separate_long_clip, stft_batch, warp, warpgrid)
 from . import parallel
 from . import bss_metrics
-from .bss_metrics import bss_eval_batch
+from .bss_metrics import bss_eval_batch, bss_eval_batch_torch
 
 __all__ = [
-    "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel", "bss_metrics", "bss_eval_batch",
+    "AvsepError", "LIB_PATH", "ops", "modules", "hotpath", "parallel", "bss_metrics", "bss_eval_batch", "bss_eval_batch_torch",
     "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
     "stft", "stft_mix", "istft", "pcm16_to_wave", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
     "_stft", "_mix_n_and_stft", "stft_batch", "Step", "clip_windows", "assemble_windows", "separate_long_clip",

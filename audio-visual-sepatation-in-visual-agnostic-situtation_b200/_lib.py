@@ -89,6 +89,8 @@ SIGNATURES = {
     "avsep_scale_if_needed": (_I, [_P, _SZ, _P, _P]),
     "avsep_pit_lossmat": (_I, [_I, _P, _P, _P, _I, _SZ, _I, _P, _P]),
     "avsep_pit_backward": (_I, [_I, _P, _P, _P, _P, _P, _I, _SZ, _I, _P, _P]),
+    "avsep_bss_eval_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "avsep_bss_eval": (_I, [_P, C.c_longlong, C.c_longlong, _P, C.c_longlong, C.c_longlong, _I, _I, _I, _I, _P, _P, _P]),
     "avsep_step_create": (_I, [c_void_pp, _I, _I, _I, _I]),
     "avsep_step_destroy": (_I, [_P]),
     "avsep_step_train_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -5,19 +5,17 @@ The reference scores every clip on the host, one at a time, through
 metrics_list=['sdr','sir','sar','si_sdr'])`` (main.py:252-275), which routes to
 ``mir_eval.separation.bss_eval_sources(compute_permutation=False)`` (BSS-eval v3, 512-tap
 distortion filters) and ``pb_bss_eval.evaluation.si_sdr``.  Once the iSTFT runs on the GPU that loop
-is the whole evaluation wall time, so this module evaluates all B clips of a batch at once, in fp64,
-where the waveforms already are:
+is the whole evaluation wall time, so all B clips of a batch are scored at once, in fp64, where the
+waveforms already are.
 
-* 131072-point real FFTs of the zero-padded references / estimates (cuFFT through ``torch.fft``),
-* the block-Toeplitz Gram matrix ``G`` [(N*512)^2] gathered from the reference cross-correlations and the
-  right-hand sides from the reference/estimate cross-correlations,
-* one batched solve per projection (Cholesky + triangular solves through ``torch.linalg``; pivoted LU, then least
-  squares, if the Gram matrix is not positive definite -- mir_eval falls back to ``lstsq`` the same way),
-* the projections as FFT convolutions and the three energy ratios.
+* ``bss_eval_batch``  -- the product path: hand-written kernels behind ``avsep_bss_eval`` (csrc/bss_eval.cu): direct
+  lag-0..511 cross-correlations, block-Toeplitz Levinson solves of the Gram systems, projection energies as quadratic
+  forms.  CUDA tensors only (there is no CPU path), float32 or float64, strided views are scored in place.
+* ``bss_eval_batch_torch`` -- the round-1 implementation through ``torch.fft`` / ``torch.linalg`` (131072-point FFT
+  correlations, dense Cholesky of the Gram matrix, FFT-convolution projections: the route mir_eval itself takes).  It is a
+  LIBRARY-built cross-check used by the tests (it also runs on CPU tensors) and is not called by the package.
 
-This row is LIBRARY-built (torch.fft / torch.linalg in float64), not a hand-written kernel: the arithmetic
-is a few dense fp64 solves per clip, which the B200's fp64 units and cuSOLVER handle; the hot path proper
-stays in csrc/.  It never imports ``oracle/``; tests compare it with the CPU restatement there.
+Neither imports ``oracle/``; tests compare both with the CPU restatement of mir_eval there.
 """
 from __future__ import annotations
 
@@ -57,13 +55,41 @@ def _db(num: torch.Tensor, den: torch.Tensor) -> torch.Tensor:
     return torch.where(den == 0, torch.full_like(num, float("inf")), 10.0 * torch.log10(num / den))
 
 
-def bss_eval_batch(reference: torch.Tensor, estimate: torch.Tensor, flen: int = FLEN) -> Dict[str, torch.Tensor]:
-    """reference, estimate: [B, N, L] (any float dtype, any device) -> dict of float64 [B, N] tensors
-    'sdr', 'sir', 'sar' (mir_eval.separation.bss_eval_sources without permutation search) and 'si_sdr'."""
+def bss_eval_batch(reference: torch.Tensor, estimate: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """reference, estimate: [B, N, L] CUDA tensors (float32 or float64; any strides with a contiguous last dimension) ->
+    dict of float64 [B, N] tensors 'sdr', 'sir', 'sar' (mir_eval.separation.bss_eval_sources without permutation search,
+    512-tap distortion filters) and 'si_sdr' (pb_bss_eval).  Hand-written kernels (csrc/bss_eval.cu), no library call."""
+    from . import _lib
+    from ._lib import check, lib
+    if reference.dim() != 3 or reference.shape != estimate.shape:
+        raise ValueError(f"bss_eval_batch: expected matching [B, N, L] tensors, got {tuple(reference.shape)} and {tuple(estimate.shape)}")
+    if not (reference.is_cuda and estimate.is_cuda):
+        raise _lib.AvsepError("bss_eval_batch: expected CUDA tensors (avsep_b200 has no CPU path); bss_eval_batch_torch is the "
+                              "library-built cross-check that also accepts CPU tensors")
+    dt = torch.float64 if (reference.dtype == torch.float64 or estimate.dtype == torch.float64) else torch.float32
+    ref = reference if reference.dtype == dt else reference.to(dt)
+    est = estimate if estimate.dtype == dt else estimate.to(dt)
+    if ref.stride(-1) != 1:
+        ref = ref.contiguous()
+    if est.stride(-1) != 1:
+        est = est.contiguous()
+    B, N, L = ref.shape
+    out = torch.empty((4, B, N), device=ref.device, dtype=torch.float64)
+    if B:
+        ws = torch.empty(int(lib.avsep_bss_eval_workspace_bytes(B, N, L)), dtype=torch.uint8, device=ref.device)
+        check(lib.avsep_bss_eval(ref.data_ptr(), ref.stride(0), ref.stride(1), est.data_ptr(), est.stride(0), est.stride(1),
+                                 int(dt == torch.float64), B, N, L, out.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream),
+              "avsep_bss_eval")
+    return dict(sdr=out[0], sir=out[1], sar=out[2], si_sdr=out[3])
+
+
+def bss_eval_batch_torch(reference: torch.Tensor, estimate: torch.Tensor, flen: int = FLEN) -> Dict[str, torch.Tensor]:
+    """LIBRARY-built cross-check of bss_eval_batch (torch.fft / torch.linalg, mir_eval's own route); any device.
+    reference, estimate: [B, N, L] -> dict of float64 [B, N] tensors 'sdr', 'sir', 'sar', 'si_sdr'."""
     ref = reference.to(torch.float64)
     est = estimate.to(torch.float64)
     if ref.dim() != 3 or ref.shape != est.shape:
-        raise ValueError(f"bss_eval_batch: expected matching [B, N, L] tensors, got {tuple(ref.shape)} and {tuple(est.shape)}")
+        raise ValueError(f"bss_eval_batch_torch: expected matching [B, N, L] tensors, got {tuple(ref.shape)} and {tuple(est.shape)}")
     B, N, L = ref.shape
     dev = ref.device
     P = L + flen - 1                                   # length of the padded signals / projections
@@ -118,7 +144,7 @@ def get_metrics(mix, clean, estimate, sample_rate: int = 11025, metrics_list: Se
     (numpy or torch), source-averaged floats back.  ``mix`` and ``sample_rate`` are accepted for signature
     compatibility; the input_* metrics asteroid also returns are not used by the reference and not computed."""
     if device is None:
-        device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        device = torch.device("cuda")
     c = torch.as_tensor(np.asarray(clean) if not torch.is_tensor(clean) else clean, dtype=torch.float64, device=device)
     e = torch.as_tensor(np.asarray(estimate) if not torch.is_tensor(estimate) else estimate, dtype=torch.float64, device=device)
     res = bss_eval_batch(c[None], e[None])

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libavsep_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["runtime.cu", "dft_plan.cu", "warp_prepare.cu", "synth_mask.cu", "loss.cu", "step.cu"]
+SOURCES = ["runtime.cu", "dft_plan.cu", "warp_prepare.cu", "synth_mask.cu", "loss.cu", "step.cu", "bss_eval.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", "-I", INCLUDE]
 

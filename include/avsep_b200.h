@@ -241,6 +241,22 @@ int avsep_pit_backward(int loss_kind, const float* preds_dev, const float* targe
                        void* stream);
 
 /* ---- end-to-end host-buffer entry points (what bench.py's `e2e` times) --------------------- */
+/* ---- separation metrics ---------------------------------------------------------------- */
+/* Replaces the per-clip metric call of calc_metrics (main.py:252-275): asteroid.metrics.get_metrics(mix, clean, estimate,
+ * sample_rate=11025, metrics_list=['sdr','sir','sar','si_sdr']) = mir_eval.separation.bss_eval_sources(compute_permutation=
+ * False) (BSS-eval v3, 512-tap distortion filters) + pb_bss_eval si_sdr, for all B clips at once, in fp64, on the device:
+ * direct lag-0..511 cross-correlations, block-Toeplitz Levinson solves of the (N*512)^2 Gram systems, projection energies as
+ * quadratic forms (csrc/bss_eval.cu).  No FFT, no dense factorisation, no library call.
+ *   ref_dev / est_dev : reference sources / estimates, float32 (is_double = 0) or float64 (1); element (b, n, t) sits at
+ *                       base[b * stride_b + n * stride_n + t], t < L  (strides in elements: waveforms of a step and its
+ *                       wav output are scored in place, without gathering)
+ *   out_dev           : double [4][B][N] = sdr, sir, sar, si_sdr per clip and source (the reference averages over sources)
+ *   workspace_dev     : avsep_bss_eval_workspace_bytes(B, N, L) bytes */
+size_t avsep_bss_eval_workspace_bytes(int B, int N, int L);
+int avsep_bss_eval(const void* ref_dev, long long ref_stride_b, long long ref_stride_n,
+                   const void* est_dev, long long est_stride_b, long long est_stride_n, int is_double,
+                   int B, int N, int L, double* out_dev, void* workspace_dev, void* stream);
+
 /* Config C2 train step through host buffers: H2D of the waveforms, STFT of all (N+1) signals,
  * prepare, synth + sigmoid + weighted BCE, full backward, D2H of the loss.
  *   waves_host [N+1, B, wave_len], SIGNAL-major: plane 0 = the B mixtures, plane 1+n = source n of every mixture
