@@ -160,9 +160,10 @@ __device__ __forceinline__ void small_solve(const double (&A)[N][N], double (&Bm
   }
 }
 
-// sum of NV doubles per thread over the CTA (256 threads), result broadcast to all threads; fixed order
+// sum of NV doubles per thread over the CTA (256 threads), result broadcast to all threads; fixed order.  The cross-warp
+// stage is done by ONE thread per value (the fp64 pipe is the bottleneck of the recursion: no redundant additions).
 template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* [8][NV] */) {
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* [9][NV] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
@@ -172,14 +173,59 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* [8
     if (lane == 0) scratch[warp * NV + q] = s;
   }
   __syncthreads();
-#pragma unroll
-  for (int q = 0; q < NV; ++q) {
+  if (threadIdx.x < NV) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += scratch[w * NV + q];
-    v[q] = s;
+    for (int w = 0; w < 8; ++w) s += scratch[w * NV + threadIdx.x];
+    scratch[8 * NV + threadIdx.x] = s;
   }
   __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = scratch[8 * NV + q];
+}
+
+// inverse of a small symmetric positive definite block: closed forms for N <= 3 (one division), elimination otherwise
+template <int N>
+__device__ __forceinline__ void small_inverse(const double (&A)[N][N], double (&inv)[N][N]) {
+  if (N == 1) {
+    inv[0][0] = 1.0 / A[0][0];
+  } else if (N == 2) {
+    const double r = 1.0 / (A[0][0] * A[1][1] - A[0][1] * A[1][0]);
+    inv[0][0] = A[1][1] * r; inv[0][1] = -A[0][1] * r;
+    inv[1][0] = -A[1][0] * r; inv[1][1] = A[0][0] * r;
+  } else if (N == 3) {
+    const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+    const double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+    const double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+    const double r = 1.0 / (A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02);
+    inv[0][0] = c00 * r;
+    inv[1][0] = c01 * r;
+    inv[2][0] = c02 * r;
+    inv[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * r;
+    inv[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * r;
+    inv[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * r;
+    inv[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * r;
+    inv[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * r;
+    inv[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * r;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) inv[i][j] = i == j ? 1.0 : 0.0;
+    small_solve<N, N>(A, inv);
+  }
+}
+template <int N, int M>
+__device__ __forceinline__ void small_mul(const double (&A)[N][N], const double (&Bm)[N][M], double (&C)[N][M]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < N; ++q) s += A[i][q] * Bm[q][j];
+      C[i][j] = s;
+    }
 }
 
 // Block Levinson recursion for the symmetric block-Toeplitz system  sum_c R(c - a) x[c] = d[a],  a = 0..F-1, with N x N blocks
@@ -254,19 +300,15 @@ __device__ void block_levinson(const double* __restrict__ Rg, const double* __re
     }
     block_sum<2 * NN + NX>(acc, scratch);
     // every thread: reflection blocks, new error covariances, solution increment (N x N work, redundantly)
-    double Kf[N][N], Kb[N][N], g[N][NR];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) { Kf[i][j] = acc[i * N + j]; Kb[i][j] = acc[NN + i * N + j]; }
-    }
-    double Df[N][N], Db[N][N];
+    double Kf[N][N], Kb[N][N], g[N][NR], Df[N][N], Db[N][N], inv[N][N];
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int j = 0; j < N; ++j) { Df[i][j] = Kf[i][j]; Db[i][j] = Kb[i][j]; }
-    small_solve<N, N>(Eb, Kf);                                 // Kf = Eb^-1 Df
-    small_solve<N, N>(Ef, Kb);                                 // Kb = Ef^-1 Db
+      for (int j = 0; j < N; ++j) { Df[i][j] = acc[i * N + j]; Db[i][j] = acc[NN + i * N + j]; }
+    small_inverse<N>(Eb, inv);
+    small_mul<N, N>(inv, Df, Kf);                              // Kf = Eb^-1 Df
+    small_inverse<N>(Ef, inv);
+    small_mul<N, N>(inv, Db, Kb);                              // Kb = Ef^-1 Db
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -277,11 +319,13 @@ __device__ void block_levinson(const double* __restrict__ Rg, const double* __re
         Ef[i][j] -= sf;                                        // Ef <- Ef - Db Kf
         Eb[i][j] -= sb;                                        // Eb <- Eb - Df Kb
       }
+    double rhs[N][NR];
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int r = 0; r < NR; ++r) g[i][r] = dv(m, i, r) - acc[2 * NN + i * NR + r];
-    small_solve<N, NR>(Eb, g);                                 // g = Eb_new^-1 (d[m] - eps)
+      for (int r = 0; r < NR; ++r) rhs[i][r] = dv(m, i, r) - acc[2 * NN + i * NR + r];
+    small_inverse<N>(Eb, inv);
+    small_mul<N, NR>(inv, rhs, g);                             // g = Eb_new^-1 (d[m] - eps)
     // Fv'[c] = Fv[c] - Bv[c - 1] Kf,  Bv'[c] = Bv[c - 1] - Fv[c] Kb   (c = 0..m; Fv[m] = 0, Bv[-1] = 0): read, sync, write
     double nf[2][NN], nb[2][NN];
 #pragma unroll
@@ -345,8 +389,8 @@ __global__ void __launch_bounds__(256) bss_solve_kernel(const BssParams p) {
   extern __shared__ double sm[];
   const int b = blockIdx.y, sys = blockIdx.x;
   const double* corr = p.corr + (size_t)b * 2 * N * N * BSS_F;
-  double* scratch = sm;                                        // [8][2 N^2 + N^2]
-  double* base = sm + 8 * 3 * N * N;
+  double* scratch = sm;                                        // [9][2 N^2 + N^2]
+  double* base = sm + 9 * 3 * N * N;
   if (sys == 0) {
     double* Fv = base;
     double* Bv = Fv + BSS_F * N * N;
@@ -397,7 +441,7 @@ __global__ void __launch_bounds__(256) bss_metric_kernel(const BssParams p) {
 
 template <int N>
 static int launch_solve(const BssParams& p, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * (8 * 3 * N * N + (size_t)BSS_F * (2 * N * N + N * N));
+  const size_t smem = sizeof(double) * (9 * 3 * N * N + (size_t)BSS_F * (2 * N * N + N * N));
   auto kern = bss_solve_kernel<N>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(1 + N, p.B), 256, smem, stream>>>(p);
