@@ -12,7 +12,7 @@ The directory name carries the upstream repo name (hyphens), so import it throug
 from . import _lib
 from ._lib import AvsepError, LIB_PATH
 from . import ops
-from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pcm16_to_wave, pit_loss, pit_lossmat, separate, stft, stft_mix,
+from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pcm16_to_wave, pit_loss, pit_lossmat, pit_reorder, pit_search, separate, stft, stft_mix,
                   synth_masks, synth_masks_loss, synth_nosum, synth_pixelwise)
 from . import modules
 from .modules import BCELoss, BaseLoss, Bias, InnerProd, L1Loss, L2Loss, PitWrapper, activate

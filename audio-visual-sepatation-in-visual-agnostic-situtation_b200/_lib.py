@@ -88,6 +88,8 @@ SIGNATURES = {
     "avsep_loss_backward": (_I, [_I, _P, _P, _P, _I, _SZ, _P, _P, _P]),
     "avsep_scale_if_needed": (_I, [_P, _SZ, _P, _P]),
     "avsep_pit_lossmat": (_I, [_I, _P, _P, _P, _I, _SZ, _I, _P, _P]),
+    "avsep_pit_search": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "avsep_pit_reorder": (_I, [_P, _P, _I, _SZ, _I, _P, _P]),
     "avsep_pit_backward": (_I, [_I, _P, _P, _P, _P, _P, _I, _SZ, _I, _P, _P]),
     "avsep_bss_eval_workspace_bytes": (_SZ, [_I, _I, _I]),
     "avsep_bss_eval": (_I, [_P, C.c_longlong, C.c_longlong, _P, C.c_longlong, C.c_longlong, _I, _I, _I, _I, _P, _P, _P]),

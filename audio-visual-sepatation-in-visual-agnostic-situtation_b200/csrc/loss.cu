@@ -1,6 +1,8 @@
 // The criterion as a stand-alone op (models/criterion.py:6-49) for predictions that do not come
 // from the synthesizer (root main.py feeds U-Net logits directly, main.py:131-136), and the
 // S x S loss matrix of PitWrapper (models/criterion.py:159-176).  Pure streaming reductions.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace avsep {
@@ -179,6 +181,66 @@ __global__ void pit_fin_kernel(const double* __restrict__ partial, int chunks, i
   lossmat[(size_t)b * SS + e] = (float)(s * inv_P);
 }
 
+// PitWrapper._fast_pit (criterion.py:113-136) on the device: one thread per sample walks the S! permutations in
+// itertools.permutations order, c = mean_i lossmat[i][perm[i]] in fp32 (as torch's .mean() of S fp32 values), keeps the
+// FIRST strict minimum (`loss > c_loss`), and writes loss, the permutation and its inverse.  No D2H of the matrix.
+__global__ void pit_search_kernel(const float* __restrict__ lossmat, int B, int S, float* __restrict__ loss, int* __restrict__ perm,
+                                  int* __restrict__ inv_perm) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* lm = lossmat + (size_t)b * S * S;
+  int cur[4] = {0, 1, 2, 3}, best_p[4] = {0, 1, 2, 3};
+  float best = 0.f;
+  bool have = false;
+  while (true) {
+    float sum = 0.f;
+    for (int i = 0; i < S; ++i) sum += lm[i * S + cur[i]];
+    const float c = sum / (float)S;
+    if (!have || best > c) {
+      best = c;
+      have = true;
+      for (int i = 0; i < S; ++i) best_p[i] = cur[i];
+    }
+    // next permutation in lexicographic order (= itertools.permutations of range(S))
+    int k = S - 2;
+    while (k >= 0 && cur[k] > cur[k + 1]) --k;
+    if (k < 0) break;
+    int l = S - 1;
+    while (cur[l] < cur[k]) --l;
+    int t = cur[k]; cur[k] = cur[l]; cur[l] = t;
+    for (int lo = k + 1, hi = S - 1; lo < hi; ++lo, --hi) { t = cur[lo]; cur[lo] = cur[hi]; cur[hi] = t; }
+  }
+  loss[b] = best;
+  for (int i = 0; i < S; ++i) {
+    perm[b * S + i] = best_p[i];
+    inv_perm[b * S + best_p[i]] = i;
+  }
+}
+
+// PitWrapper.reorder_tensor (criterion.py:180-200): y[b, ..., s] = x[b, ..., perm[b][s]], one streaming pass
+template <int S>
+__global__ void __launch_bounds__(256) pit_reorder_kernel(const float* __restrict__ x, const int* __restrict__ perm, size_t P,
+                                                          float* __restrict__ y) {
+  const int b = blockIdx.y;
+  int pm[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) pm[s] = perm[b * S + s];
+  const float* xb = x + (size_t)b * P * S;
+  float* yb = y + (size_t)b * P * S;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+    float v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = xb[i * S + s];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float o = v[0];
+#pragma unroll
+      for (int q = 1; q < S; ++q) o = pm[s] == q ? v[q] : o;
+      yb[i * S + s] = o;
+    }
+  }
+}
+
 }  // namespace avsep
 
 using namespace avsep;
@@ -295,6 +357,35 @@ int avsep_pit_backward(int loss_kind, const float* preds_dev, const float* targe
     case 2: pit_bwd_kernel<2><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
     case 3: pit_bwd_kernel<3><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
     default: pit_bwd_kernel<4><<<grid, 256, 0, stream>>>(loss_kind, preds_dev, targets_dev, weights_dev, inv_perm_dev, gloss_dev, P, dpreds_dev); break;
+  }
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+int avsep_pit_search(const float* lossmat_dev, int B, int S, float* loss_dev, int* perm_dev, int* inv_perm_dev, void* stream) {
+  AVSEP_REQUIRE(lossmat_dev && loss_dev && perm_dev && inv_perm_dev, "avsep_pit_search: null tensor");
+  AVSEP_REQUIRE(S >= 1 && S <= 4 && B >= 0, "avsep_pit_search: bad B = %d / S = %d (S in [1, 4])", B, S);
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  pit_search_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(lossmat_dev, B, S, loss_dev, perm_dev, inv_perm_dev);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+int avsep_pit_reorder(const float* x_dev, const int* perm_dev, int B, size_t P, int S, float* y_dev, void* stream_) {
+  AVSEP_REQUIRE(x_dev && perm_dev && y_dev, "avsep_pit_reorder: null tensor");
+  AVSEP_REQUIRE(S >= 1 && S <= 4 && B >= 0 && B <= 65535 && P >= 1, "avsep_pit_reorder: bad B / P / S");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 1024), B);
+  switch (S) {
+    case 1: pit_reorder_kernel<1><<<grid, 256, 0, stream>>>(x_dev, perm_dev, P, y_dev); break;
+    case 2: pit_reorder_kernel<2><<<grid, 256, 0, stream>>>(x_dev, perm_dev, P, y_dev); break;
+    case 3: pit_reorder_kernel<3><<<grid, 256, 0, stream>>>(x_dev, perm_dev, P, y_dev); break;
+    default: pit_reorder_kernel<4><<<grid, 256, 0, stream>>>(x_dev, perm_dev, P, y_dev); break;
   }
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;

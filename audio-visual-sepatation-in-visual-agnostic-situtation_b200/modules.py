@@ -118,8 +118,9 @@ class PitWrapper(nn.Module):
 
     forward(preds [B,...,S], targets, weights) -> (loss [B], perms): the S x S loss matrix of every sample is
     computed by one kernel over the whole batch (the reference loops over samples and materialises [H,W,S,S]
-    repeats), the S! search runs on the tiny [B,S,S] result, and the gradient flows back to `preds` through one
-    streaming kernel.  `base_loss` may be the string 'bce' / 'l1' / 'l2' or F.binary_cross_entropy (as the
+    repeats), the S! search by a second kernel on the device (no D2H, no stream synchronisation: `perms` is a
+    device-backed sequence that only copies when Python reads its values), and the gradient flows back to `preds`
+    through one streaming kernel.  `base_loss` may be the string 'bce' / 'l1' / 'l2' or F.binary_cross_entropy (as the
     reference passes it)."""
 
     def __init__(self, base_loss="bce"):
@@ -127,9 +128,8 @@ class PitWrapper(nn.Module):
         self.kind = base_loss if isinstance(base_loss, str) else "bce"
 
     def reorder_tensor(self, tensor, p):
-        idx = torch.as_tensor(p, device=tensor.device, dtype=torch.long)           # [B, S]
-        view = idx.view(idx.shape[0], *([1] * (tensor.dim() - 2)), idx.shape[1]).expand_as(tensor)
-        return torch.gather(tensor, tensor.dim() - 1, view)
+        """criterion.py:180-200; `p` is what forward() returned (device-backed) or any list of tuples."""
+        return ops.pit_reorder(tensor, p)
 
     def forward(self, preds, targets, weights=None):
         if weights is None:

@@ -578,26 +578,58 @@ def pit_lossmat(kind: str, preds: torch.Tensor, targets: torch.Tensor, weights: 
     return out
 
 
-def _pit_search(lossmat_host: torch.Tensor):
-    """Brute-force permutation search of PitWrapper._fast_pit (criterion.py:113-136) on the host [B,S,S] matrix:
-    itertools order, first minimum wins.  Returns (losses, perms, inverse perms)."""
-    from itertools import permutations
-    B, S = lossmat_host.shape[0], lossmat_host.shape[1]
-    idx = list(range(S))
-    losses, perms, inv = [], [], []
-    for b in range(B):
-        best, best_p = None, None
-        for perm in permutations(idx):
-            c = lossmat_host[b, idx, list(perm)].mean()
-            if best is None or best > c:
-                best, best_p = c, perm
-        losses.append(float(best))
-        perms.append(best_p)
-        ip = [0] * S
-        for i, j in enumerate(best_p):
-            ip[j] = i
-        inv.append(ip)
-    return losses, perms, inv
+class Perms:
+    """The optimal permutations of a batch, kept on the device: `tensor` is int32 [B, S].  Behaves like the reference's
+    `perms` (a list of tuples: len(), indexing, iteration, ==) but only copies to the host -- one synchronising D2H of
+    B * S integers -- when Python actually looks at the values; PitWrapper.reorder_tensor consumes it on the device."""
+
+    def __init__(self, tensor: torch.Tensor, inverse: torch.Tensor):
+        self.tensor = tensor
+        self.inverse = inverse
+        self._host = None
+
+    def tolist(self):
+        if self._host is None:
+            self._host = [tuple(p) for p in self.tensor.tolist()]
+        return self._host
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+    def __getitem__(self, i):
+        return self.tolist()[i]
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def __eq__(self, other):
+        return self.tolist() == [tuple(p) for p in other]
+
+    def __repr__(self):
+        return repr(self.tolist())
+
+
+def pit_search(lossmat: torch.Tensor):
+    """PitWrapper._fast_pit (criterion.py:113-136) for the whole batch on the device: [B,S,S] -> (loss [B], Perms)."""
+    lm = _cuda_f32(lossmat, "pit_search: lossmat")
+    B, S = lm.shape[0], lm.shape[1]
+    loss = torch.empty(B, device=lm.device, dtype=torch.float32)
+    perm = torch.empty((B, S), device=lm.device, dtype=torch.int32)
+    inv = torch.empty((B, S), device=lm.device, dtype=torch.int32)
+    check(lib.avsep_pit_search(lm.data_ptr(), B, S, loss.data_ptr(), perm.data_ptr(), inv.data_ptr(), _stream()), "avsep_pit_search")
+    return loss, Perms(perm, inv)
+
+
+def pit_reorder(tensor: torch.Tensor, perms) -> torch.Tensor:
+    """PitWrapper.reorder_tensor (criterion.py:180-200): out[b, ..., s] = tensor[b, ..., perms[b][s]]."""
+    x = _cuda_f32(tensor, "pit_reorder: tensor")
+    B, S = x.shape[0], x.shape[-1]
+    pt = perms.tensor if isinstance(perms, Perms) else torch.as_tensor([list(p) for p in perms], dtype=torch.int32, device=x.device)
+    if tuple(pt.shape) != (B, S):
+        raise _lib.AvsepError(f"pit_reorder: {tuple(pt.shape)} permutations for a tensor of shape {tuple(x.shape)}")
+    y = torch.empty_like(x)
+    check(lib.avsep_pit_reorder(x.data_ptr(), pt.contiguous().data_ptr(), B, x[0].numel() // S, S, y.data_ptr(), _stream()), "avsep_pit_reorder")
+    return y
 
 
 class _PitLoss(torch.autograd.Function):
@@ -624,14 +656,14 @@ class _PitLoss(torch.autograd.Function):
 def pit_loss(kind: str, preds: torch.Tensor, targets: torch.Tensor, weights: torch.Tensor):
     """PitWrapper.forward (criterion.py:202-231): returns (loss [B], differentiable in preds; perms list of tuples).
 
-    The S x S loss matrix of every sample comes from one kernel; the S! search runs on the host [B,S,S] result."""
+    The S x S loss matrix of every sample comes from one kernel, the S! search from another: nothing is copied to the
+    host and the stream is never synchronised; `perms` is a device-backed sequence (ops.Perms)."""
     p = _cuda_f32(preds, "pit: preds")
     t = _cuda_f32(targets, "pit: targets")
     w = _cuda_f32(weights, "pit: weights")
     lm = pit_lossmat(kind, p, t, w)
-    losses, perms, inv = _pit_search(lm.double().cpu())
-    inv_t = torch.tensor(inv, dtype=torch.int32, device=p.device)
-    loss_t = torch.tensor(losses, dtype=torch.float32, device=p.device)
+    loss_t, perms = pit_search(lm)
+    inv_t = perms.inverse
     if preds.requires_grad and torch.is_grad_enabled():
         if preds.data_ptr() != p.data_ptr():                         # preds was copied (non-contiguous / unaligned): keep the graph
             return _PitLoss.apply(kind, preds.contiguous(), t, w, inv_t, loss_t), perms

@@ -234,6 +234,13 @@ int avsep_scale_if_needed(float* x_dev, size_t n, const float* gscale_dev, void*
 int avsep_pit_lossmat(int loss_kind, const float* preds_dev, const float* targets_dev,
                       const float* weights_dev, int B, size_t P, int S, float* lossmat_dev, void* stream);
 
+/* PitWrapper._fast_pit (models/criterion.py:113-136) on the device: for every sample the S! permutations in
+ * itertools.permutations order, cost = mean_i lossmat[b][i][perm[i]] in fp32, first strict minimum wins.
+ *   lossmat_dev [B,S,S] -> loss_dev [B], perm_dev [B,S] (int32), inv_perm_dev [B,S] (int32; what avsep_pit_backward takes).
+ * No D2H copy, no host synchronisation. */
+int avsep_pit_search(const float* lossmat_dev, int B, int S, float* loss_dev, int* perm_dev, int* inv_perm_dev, void* stream);
+/* PitWrapper.reorder_tensor (models/criterion.py:180-200): y[b, ..., s] = x[b, ..., perm[b][s]] for x [B, P, S]. */
+int avsep_pit_reorder(const float* x_dev, const int* perm_dev, int B, size_t P, int S, float* y_dev, void* stream);
 /* Backward of the PIT loss  loss[b] = (1/S) sum_i lossmat[b][i][perm_b[i]]  w.r.t. preds:
  *   inv_perm_dev [B, S] int32: inv_perm[b][j] = the target index matched with prediction j;  gloss_dev [B]. */
 int avsep_pit_backward(int loss_kind, const float* preds_dev, const float* targets_dev, const float* weights_dev,

@@ -395,6 +395,37 @@ def test_pit_matches_reference_golden(golden):
         (loss * torch.tensor([1.0, 2.0, 0.5], device="cuda")).sum().backward()
         assert relerr(tpr.grad.cpu().numpy(), g[f"S{S}_grad"]) < 1e-5
         assert relerr(loss.detach().cpu().numpy(), g[f"S{S}_loss"]) < 1e-5
-        assert np.array_equal(np.asarray(perms), g[f"S{S}_perms"])
+        assert isinstance(perms, av.ops.Perms) and perms.tensor.is_cuda           # the search ran on the device
+        assert len(perms) == 3 and isinstance(perms[0], tuple)
+        assert np.array_equal(np.asarray(list(perms)), g[f"S{S}_perms"])
         re = pw.reorder_tensor(_cuda(pr), perms).cpu().numpy()
-        assert np.array_equal(re, O.pit_reorder(pr, perms))
+        assert np.array_equal(re, O.pit_reorder(pr, list(perms)))
+        # reorder_tensor also takes the reference's plain list of tuples
+        assert np.array_equal(pw.reorder_tensor(_cuda(pr), [tuple(p_) for p_ in g[f"S{S}_perms"]]).cpu().numpy(), re)
+
+
+def test_pit_search_on_device_matches_itertools_order():
+    """avsep_pit_search against the reference's _fast_pit loop (criterion.py:113-136): itertools.permutations order, fp32
+    mean, first strict minimum -- including exact ties, which the first permutation must win."""
+    from itertools import permutations
+    r = np.random.default_rng(3)
+    for S in (1, 2, 3, 4):
+        lm = r.random((37, S, S)).astype(np.float32)
+        lm[5] = 0.25                                                 # all permutations tie: the identity wins
+        if S >= 2:
+            lm[7] = lm[7, ::-1].copy()
+        loss, perms = av.ops.pit_search(_cuda(lm))
+        want_p, want_l = [], []
+        for b in range(lm.shape[0]):
+            best, bp = None, None
+            t = torch.from_numpy(lm[b])
+            for p_ in permutations(range(S)):
+                c = t[range(S), p_].mean()
+                if best is None or best > c:
+                    best, bp = c, p_
+            want_p.append(bp); want_l.append(float(best))
+        assert list(perms) == want_p
+        assert np.allclose(loss.cpu().numpy(), np.array(want_l, dtype=np.float32), rtol=1e-7, atol=0)
+        inv = perms.inverse.cpu().numpy()
+        for b, p_ in enumerate(want_p):
+            assert all(inv[b][p_[i]] == i for i in range(S))
