@@ -18,8 +18,9 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libavsep_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["runtime.cu", "dft_plan.cu", "warp_prepare.cu", "synth_mask.cu", "loss.cu", "step.cu", "bss_eval.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", "-I", INCLUDE]
+BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
+NVCC_FLAGS = BASE_FLAGS + ["-I", INCLUDE]
 
 
 def _nvcc() -> str:
@@ -37,7 +38,7 @@ def _fingerprint() -> str:
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(BASE_FLAGS).encode())        # not the -I path: the checkout lives elsewhere on the GPU box
     return h.hexdigest()
 
 
@@ -48,6 +49,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts several ranks at once); the others wait, then find the fingerprint current
+    import fcntl
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
+            return LIB
+        return _build_locked(fp, stamp, verbose)
+
+
+def _build_locked(fp: str, stamp: str, verbose: bool) -> str:
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
@@ -65,10 +76,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)                            # atomic: a concurrent dlopen sees the old or the new file, never half of one
     with open(stamp, "w") as f:
         f.write(fp)
     return LIB

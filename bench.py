@@ -297,20 +297,25 @@ class Reducer:
     def __init__(self, dist, world, dev, width, slots=8):
         self.dist, self.world = dist, world
         self.buf = torch.zeros((slots, width), device=dev)
+        self.staged = torch.zeros((slots, width), device=dev)      # per-slot input: [src..., weight], the weight column written once
         self.work = [None] * slots
         self.i = 0
         self.count = 0
+        self.weight = None
 
     def push(self, src, weight):
         """Reduce [src..., weight] of this step; src is a small device tensor the step has just written."""
         if self.world == 1:
             return
+        if self.weight != weight:                                  # (re)write the constant weight column of every slot
+            self.staged[:, src.numel():] = float(weight)
+            self.weight = weight
         k = self.i % len(self.work)
         if self.work[k] is not None:
             self.work[k].wait()                                    # stream-level wait, the host is not blocked
         slot = self.buf[k]
-        slot[:src.numel()].copy_(src.reshape(-1), non_blocking=True)          # D2D memcpy on the step's stream
-        slot[src.numel():].fill_(float(weight))
+        slot.copy_(self.staged[k], non_blocking=True)              # D2D memcpys on the step's stream: the weight column ...
+        slot[:src.numel()].copy_(src.reshape(-1), non_blocking=True)          # ... and the step's own sums
         self.work[k] = self.dist.all_reduce(slot, async_op=True)
         self.i += 1
         self.count += 1
