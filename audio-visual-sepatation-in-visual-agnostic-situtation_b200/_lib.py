@@ -59,11 +59,8 @@ SIGNATURES = {
     "avsep_plan_frames": (_I, [_P]),
     "avsep_plan_istft_len": (_I, [_P]),
     "avsep_plan_workspace_bytes": (_SZ, [_P]),
-    "avsep_plan_set_kblock": (_I, [_P, _I]),
     "avsep_plan_set_fold": (_I, [_P, _I]),
-    "avsep_plan_set_two_cta": (_I, [_P, _I]),
     "avsep_plan_set_inverse_fold": (_I, [_P, _I]),
-    "avsep_plan_set_fused_stage": (_I, [_P, _I, _I]),
     "avsep_plan_set_mix_linear": (_I, [_P, _I]),
     "avsep_stft_mix": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "avsep_stft": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),

@@ -1,14 +1,13 @@
-// Forward STFT as a FOLDED split-precision tcgen05 GEMM: half the tensor work of dft_gemm.cuh.
+// Forward STFT as a FOLDED split-precision tcgen05 GEMM: half the tensor work of the plain GEMM in dft_gemm.cuh.
 //
 // For a real frame x[0..1021] and the symmetric periodic Hann window w (w[n] = w[1022 - n]):
 //   Re X[f] =  sum_{n=0}^{511} w[n] cos(2 pi f n / 1022) * E[n],   E[n] = x[n] + x[1022 - n]  (E[0] = x[0], E[511] = x[511])
 //   Im X[f] = -sum_{n=1}^{510} w[n] sin(2 pi f n / 1022) * O[n],   O[n] = x[n] - x[1022 - n]  (O[0] = O[511] = 0)
 // so the 1024 x 1024 x T contraction per signal becomes two 512 x 512 x T ones (cos rows x E, sin rows x O).
 //
-// Tile = 128 bins x 128 frames (UMMA M = 128, N = 128).  Accumulator buffer b holds Re in TMEM columns
-// [256 b, 256 b + 128) and Im in [256 b + 128, 256 b + 256) of the SAME lanes, so an epilogue thread owns (re, im)
-// of its bin without any exchange, and the two buffers let the epilogue of tile i overlap the MMAs of tile i + 1.
-//   warp 0: TMA producer | warp 1: TMEM allocator + MMA issuer | warps 2..9: epilogue (2 per TMEM lane group)
+// Two kernels, both CTA pairs (cta_group::2) that GENERATE the E / O operand themselves from the fp32 waveform:
+//   dft_fold3_fwd_kernel   any batch of signals (eval step, stft / stft_mix with phase or (re, im) outputs)
+//   dft_fold3m_fwd_kernel  two-source mixtures formed on the device: the training step (mixture spectrum = X0 + X1)
 #pragma once
 #include <cuda.h>
 
@@ -24,19 +23,6 @@ constexpr int FOLD_M_TILES = FOLD_BINS / FOLD_TILE_M;   // 4
 constexpr int FOLD_THREADS = 320;
 constexpr int FOLD_SMEM_LIMIT = 232448;
 
-template <int BK>
-struct FoldCfg {
-  static_assert(BK == 32 || BK == 64, "K block is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
-  static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int A_BYTES = FOLD_TILE_M * ROW_BYTES;
-  static constexpr int B_BYTES = FOLD_TILE_N * ROW_BYTES;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
-  static constexpr int KB_HALF = FOLD_K / BK;          // k-blocks per accumulator (Re, then Im)
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
-};
-
 struct FoldParams {
   int num_signals;
   int T;
@@ -51,409 +37,28 @@ struct FoldParams {
   int reim_count;
   int prefetch;      // L2-prefetch the next tile's operand while loading the current one
   int* err_flag;
-  // dft_fold3_fwd_kernel only: the raw fp32 waveforms (the E / O operand is generated inside the kernel)
-  const float* wave; // [S, L]
+  const float* wave; // [S, L] fp32 waveforms (the E / O operand is generated inside the kernel)
   int L;
+  // device-summed mixtures (dft_fold3): signals s < mix_B are read from wave_mix [mix_B, L], signal s >= mix_B is
+  // wave[s - mix_B] (the sources); mix_B = 0: every signal comes from `wave`
+  const float* wave_mix;
+  int mix_B;
 };
 
-// basis tensor map: rows = (kind * 2 + split) * 512 + f, cols = n (512)        kind 0 = cos, 1 = -sin
-// operand tensor map: dims (n = 512, t = T, plane = (kind * 2 + split) * s_cap + s)   kind 0 = E, 1 = O
-template <int BK>
-__global__ void __launch_bounds__(FOLD_THREADS, 1)
-dft_fold_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FoldParams p) {
-  using Cfg = FoldCfg<BK>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);
-    }
-    fence_mbar_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m = tile % FOLD_M_TILES;
-        const int rest = tile / FOLD_M_TILES;
-        const int nt = rest % p.n_tiles;
-        const int s = rest / p.n_tiles;
-        // The staged E / O planes (1 MB per signal) do not stay in L2 between the staging kernel and this one:
-        // while loading k-block kb of this tile, pull k-block kb of the NEXT tile into L2 (a whole tile time ahead,
-        // interleaved with the demand loads so the prefetches never queue in front of them).
-        const int next = tile + gridDim.x;
-        const bool has_next = next < p.total_tiles;
-        const int nrest = next / FOLD_M_TILES;
-        const int nnt = nrest % p.n_tiles, ns = nrest / p.n_tiles;
-        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
-          const int kind = kb / Cfg::KB_HALF;                 // 0: cos x E -> Re, 1: -sin x O -> Im
-          const int k0 = (kb % Cfg::KB_HALF) * BK;
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 11);
-          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          tma_load_2d(&tmA, full_bar(stage), st, k0, (kind * 2 + 0) * FOLD_BINS + m * FOLD_TILE_M);
-          tma_load_2d(&tmA, full_bar(stage), st + Cfg::A_BYTES, k0, (kind * 2 + 1) * FOLD_BINS + m * FOLD_TILE_M);
-          tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES, k0, nt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + s);
-          tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, nt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + s);
-          if (has_next && p.prefetch) {
-            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 0) * p.s_cap + ns);
-            tma_prefetch_3d(&tmB, k0, nnt * FOLD_TILE_N, (kind * 2 + 1) * p.s_cap + ns);
-          }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(FOLD_TILE_M, FOLD_TILE_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 12);
-        tcgen05_fence_after();
-        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
-          const int kind = kb / Cfg::KB_HALF;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * FOLD_TILE_N + kind * FOLD_TILE_N);
-          const bool first = (kb % Cfg::KB_HALF) == 0;
-          mbar_wait(full_bar(stage), phase, p.err_flag, 13);
-          tcgen05_fence_after();
-          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint64_t a_hi = umma_smem_desc(st, Cfg::ROW_BYTES);
-          const uint64_t a_lo = umma_smem_desc(st + Cfg::A_BYTES, Cfg::ROW_BYTES);
-          const uint64_t b_hi = umma_smem_desc(st + 2 * Cfg::A_BYTES, Cfg::ROW_BYTES);
-          const uint64_t b_lo = umma_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::ROW_BYTES);
-#pragma unroll
-          for (int k16 = 0; k16 < BK / 16; ++k16) {
-            const uint64_t adv = (uint64_t)(k16 * 2);
-            umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, (first && k16 == 0) ? 0u : 1u);
-            umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-          }
-          umma_commit(empty_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================================== epilogue (8 warps) ================================
-    const int q = warp & 3;                 // TMEM lane group this warp may touch
-    const int half = (warp - 2) >> 2;       // which 64 of the 128 frame columns
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m = tile % FOLD_M_TILES;
-      const int rest = tile / FOLD_M_TILES;
-      const int nt = rest % p.n_tiles;
-      const int s = rest / p.n_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 14);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * FOLD_TILE_N);
-      const int f = FOLD_TILE_M * m + 32 * q + lane;
-      const size_t row_off = ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f) * (size_t)p.T;
-      const bool vec_ok = (p.T & 3) == 0;
-      const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-        const int t0 = nt * FOLD_TILE_N + c0;
-        if (t0 >= p.T) break;
-        uint32_t vr[32], vi[32];
-        tmem_ld_32x32b_x32(taddr + c0, vr);
-        tmem_ld_32x32b_x32(taddr + FOLD_TILE_N + c0, vi);
-        tmem_ld_wait();
-        if (vec_ok && t0 + 32 <= p.T) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float rr[4], ii[4], mg[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              rr[e] = __uint_as_float(vr[j + e]);
-              ii[e] = __uint_as_float(vi[j + e]);
-              mg[e] = sqrtf(fmaf(rr[e], rr[e], ii[e] * ii[e]));
-            }
-            __stcs(reinterpret_cast<float4*>(p.mag + row_off + t0 + j), make_float4(mg[0], mg[1], mg[2], mg[3]));
-            if (p.phase)
-              *reinterpret_cast<float4*>(p.phase + row_off + t0 + j) =
-                  make_float4(atan2f(ii[0], rr[0]), atan2f(ii[1], rr[1]), atan2f(ii[2], rr[2]), atan2f(ii[3], rr[3]));
-            if (want_reim) {
-              *reinterpret_cast<float4*>(p.re + row_off + t0 + j) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-              *reinterpret_cast<float4*>(p.im + row_off + t0 + j) = make_float4(ii[0], ii[1], ii[2], ii[3]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (t0 + j < p.T) {
-              const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
-              p.mag[row_off + t0 + j] = sqrtf(fmaf(rr, rr, ii * ii));
-              if (p.phase) p.phase[row_off + t0 + j] = atan2f(ii, rr);
-              if (want_reim) { p.re[row_off + t0 + j] = rr; p.im[row_off + t0 + j] = ii; }
-            }
-          }
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+// waveform of signal s of a dft_fold3 launch
+__device__ __forceinline__ const float* fold3_signal(const FoldParams& p, int s) {
+  return s < p.mix_B ? p.wave_mix + (size_t)s * p.L : p.wave + (size_t)(s - p.mix_B) * p.L;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// CTA-pair version of the folded transform (cta_group::2): one 256-bin x 256-frame tile per pair of SMs.
-// Each CTA stages its own 128 bins of the basis and 128 of the 256 frames; the pair's MMA has M = 256, N = 256,
-// so per SM the shared-memory traffic (operand reads + TMA writes) drops from ~158 to ~106 B/clk, below the
-// 128 B/clk limit that caps the single-CTA kernels.  Re accumulates in TMEM columns [0, 256), Im in [256, 512)
-// of each CTA's own 128 lanes; with all 512 columns in use the epilogue (8 warps per CTA) is not overlapped.
-constexpr int FOLD2_TILE_N = 256;
-
-template <int BK>
-struct Fold2Cfg {
-  static_assert(BK == 32 || BK == 64, "K block is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
-  static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int A_BYTES = FOLD_TILE_M * ROW_BYTES;
-  static constexpr int B_BYTES = (FOLD2_TILE_N / 2) * ROW_BYTES;     // this CTA's 128 frames
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int XPOSE_BYTES = 8 * 32 * 33 * 4;                // one padded 32 x 32 transpose tile per epilogue warp
-  static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256 - XPOSE_BYTES) / STAGE_BYTES;
-  static constexpr int KB_HALF = FOLD_K / BK;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + XPOSE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
-  static_assert(STAGES >= 2 && (2 * STAGES + 3) * 8 <= 256, "barrier block overflow");
-};
-
-template <int BK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD_THREADS, 1)
-dft_fold2_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FoldParams p) {
-  using Cfg = Fold2Cfg<BK>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* xpose_all = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
-  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
-  const uint32_t tempty_bar = bar_base + 8u * (2 * Cfg::STAGES + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 2));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1;
-  const int npairs = gridDim.x >> 1;
-  const int n_tiles = (p.T + FOLD2_TILE_N - 1) / FOLD2_TILE_N;
-  const int pair_tiles = p.num_signals * n_tiles * (FOLD_M_TILES / 2);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 512);                   // 256 epilogue threads of each CTA of the pair
-    fence_mbar_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) {
-    tmem_alloc2(tmem_slot, 512);
-    tmem_relinquish2();
-  }
-  tcgen05_fence_before();
-  cluster_sync_all();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    // ===================================== TMA producer (both CTAs) ==========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < pair_tiles; tile += npairs) {
-        const int mp = tile % (FOLD_M_TILES / 2);
-        const int rest = tile / (FOLD_M_TILES / 2);
-        const int nt = rest % n_tiles;
-        const int s = rest / n_tiles;
-        const int row0 = (2 * mp + (int)rank) * FOLD_TILE_M;
-        const int t0 = nt * FOLD2_TILE_N + (int)rank * (FOLD2_TILE_N / 2);
-        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
-          const int kind = kb / Cfg::KB_HALF;
-          const int k0 = (kb % Cfg::KB_HALF) * BK;
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 31);
-          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-          tma2_load_2d(&tmA, lead_full, st, k0, (kind * 2 + 0) * FOLD_BINS + row0);
-          tma2_load_2d(&tmA, lead_full, st + Cfg::A_BYTES, k0, (kind * 2 + 1) * FOLD_BINS + row0);
-          tma2_load_3d(&tmB, lead_full, st + 2 * Cfg::A_BYTES, k0, t0, (kind * 2 + 0) * p.s_cap + s);
-          tma2_load_3d(&tmB, lead_full, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, t0, (kind * 2 + 1) * p.s_cap + s);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================================== MMA issuer (leader CTA only) =======================
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, FOLD2_TILE_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t tile_phase = 0;
-      for (int tile = pair; tile < pair_tiles; tile += npairs) {
-        mbar_wait(tempty_bar, tile_phase ^ 1u, p.err_flag, 32);
-        tcgen05_fence_after();
-        for (int kb = 0; kb < 2 * Cfg::KB_HALF; ++kb) {
-          const int kind = kb / Cfg::KB_HALF;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(kind * FOLD2_TILE_N);
-          const bool first = (kb % Cfg::KB_HALF) == 0;
-          mbar_wait(full_bar(stage), phase, p.err_flag, 33);
-          tcgen05_fence_after();
-          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint64_t a_hi = umma_smem_desc(st, Cfg::ROW_BYTES);
-          const uint64_t a_lo = umma_smem_desc(st + Cfg::A_BYTES, Cfg::ROW_BYTES);
-          const uint64_t b_hi = umma_smem_desc(st + 2 * Cfg::A_BYTES, Cfg::ROW_BYTES);
-          const uint64_t b_lo = umma_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::ROW_BYTES);
-#pragma unroll
-          for (int k16 = 0; k16 < BK / 16; ++k16) {
-            const uint64_t adv = (uint64_t)(k16 * 2);
-            umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (first && k16 == 0) ? 0u : 1u);
-            umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-          }
-          umma_commit_2sm(empty_bar(stage), 3);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit_2sm(tfull_bar, 3);
-        tile_phase ^= 1u;
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================================== epilogue (8 warps per CTA, own 128 bins) ===========
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;             // which 128 of the 256 frame columns
-    const uint32_t lead_tempty = mapa_shared(tempty_bar, 0);
-    uint32_t tile_phase = 0;
-    for (int tile = pair; tile < pair_tiles; tile += npairs) {
-      const int mp = tile % (FOLD_M_TILES / 2);
-      const int rest = tile / (FOLD_M_TILES / 2);
-      const int nt = rest % n_tiles;
-      const int s = rest / n_tiles;
-      mbar_wait(tfull_bar, tile_phase, p.err_flag, 34);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;        // first bin of this warp's 32 TMEM lanes
-      float* xt = xpose_all + (warp - 2) * (32 * 33);
-      const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
-      // A lane owns one bin (row); a plain store would scatter 32 rows per instruction.  Each 32 x 32 block is
-      // transposed through a padded shared-memory tile so that every store instruction writes 128 contiguous bytes.
-      auto store_block = [&](float* __restrict__ dst, const float (&val)[32], int t0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xt[lane * 33 + j] = val[j];
-        __syncwarp();
-        const int t = t0 + lane;
-        if (t < p.T) {
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) __stcs(dst + ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0 + r) * (size_t)p.T + t, xt[r * 33 + lane]);
-        }
-        __syncwarp();
-      };
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-        const int t0 = nt * FOLD2_TILE_N + c0;
-        if (t0 >= p.T) break;
-        uint32_t vr[32], vi[32];
-        tmem_ld_32x32b_x32(taddr + c0, vr);
-        tmem_ld_32x32b_x32(taddr + FOLD2_TILE_N + c0, vi);
-        tmem_ld_wait();
-        float val[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
-          val[j] = sqrtf(fmaf(rr, rr, ii * ii));
-        }
-        store_block(p.mag, val, t0);
-        if (p.phase) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = atan2f(__uint_as_float(vi[j]), __uint_as_float(vr[j]));
-          store_block(p.phase, val, t0);
-        }
-        if (want_reim) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vr[j]);
-          store_block(p.re, val, t0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vi[j]);
-          store_block(p.im, val, t0);
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive_cluster_relaxed(lead_tempty);
-      tile_phase ^= 1u;
-    }
-  }
-
-  tcgen05_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc2(tmem_base, 512);
-  }
-}
+constexpr int FOLD2_TILE_N = 256;      // frames per pair tile of dft_fold3
 
 // ======================================================================================================
 // dft_fold3: the CTA-pair folded GEMM with the E / O operand GENERATED IN THE KERNEL from the raw waveform.
 //
-// dft_fold2 reads E[n] = x[n] + x[1022 - n], O[n] = x[n] - x[1022 - n] (bf16 hi / lo) from planes that
-// wave_fold_kernel staged in HBM: 1 MB written and read back per signal, 4x the waveform itself, because folded
-// frames no longer overlap.  Here NPW producer warps per CTA read the fp32 waveform (63 MB for 240 signals: it
-// stays in L2), fold, split and store straight into the swizzled shared-memory tile the MMA reads, so the
-// staging kernel and its 2 x 252 MB of HBM traffic disappear.
+// Staging E[n] = x[n] + x[1022 - n], O[n] = x[n] - x[1022 - n] (bf16 hi / lo) in HBM would cost 1 MB written and read back
+// per signal, 4x the waveform itself, because folded frames no longer overlap (round 1 measured that variant: 0.25 ms for
+// 240 signals against 0.20 ms here).  Instead NPW producer warps per CTA read the fp32 waveform (63 MB for 240 signals: it
+// stays in L2), fold, split and store straight into the swizzled shared-memory tile the MMA reads.
 //
 // Stage (64 KB, K block 32, SWIZZLE_64B, both kinds so one waveform load feeds E and O):
 //   [cos hi | cos lo | -sin hi | -sin lo]  4 x 8 KB, this CTA's 128 bins, by TMA from the basis
@@ -589,7 +194,7 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
       const int rest = tile / (FOLD_M_TILES / 2);
       const int nt = rest % n_tiles;
       const int s = rest / n_tiles + p.sig_base;
-      const float* w = p.wave + (size_t)s * p.L;
+      const float* w = fold3_signal(p, s);
       const int t_first = nt * FOLD2_TILE_N + (int)rank * (FOLD2_TILE_N / 2);
       const int lo = max(t_first * AVSEP_HOP - AVSEP_N_FFT / 2, 0);
       const int hi = min((t_first + FOLD2_TILE_N / 2 - 1) * AVSEP_HOP + AVSEP_N_FFT / 2, p.L - 1);
@@ -680,7 +285,7 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
         const int rest = tile / (FOLD_M_TILES / 2);
         const int nt = rest % n_tiles;
         const int s = rest / n_tiles + p.sig_base;
-        w = p.wave + (size_t)s * p.L;
+        w = fold3_signal(p, s);
         tbase = nt * FOLD2_TILE_N + (int)rank * (FOLD2_TILE_N / 2) + r0 + sub;
         // bit i: both frames of iteration i lie in [2, (L - 512) / 256], where no sample index leaves the signal
         lin_mask = 0;

@@ -9,11 +9,13 @@
 // hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators, which holds the 1e-4 tolerance of the north star
 // for n_fft = 1022 (K padded to 1024 with two zero basis columns).
 //
-// One CTA per SM, persistent over (signal, frame-tile, row-tile) work items; 128 x 256 output tile
-// (UMMA M=128, N=256, K=16), K pipelined in BK-wide stages filled by TMA (64B or 128B swizzle),
-// two 256-column TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+// This PLAIN (unfolded) GEMM is the in-library cross-check of the folded product kernels (dft_fold.cuh, idft_fold.cuh) and
+// the raw-accumulator debug hook; round 1 shipped it as the inverse transform.  CTA pairs (cta_group::2), persistent over
+// (signal, frame-tile, row-tile) work items, 256 x 256 output tile per pair (UMMA M=256, N=256, K=16), K pipelined in
+// 64-wide stages filled by TMA (128B swizzle), two 256-column TMEM accumulator buffers so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
 //   warp 0      : TMA producer (one elected lane)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane of the leader CTA)
 //   warps 2..5  : epilogue (each owns the 32 TMEM lanes selected by warp_id % 4)
 #pragma once
 #include <cuda.h>
@@ -33,21 +35,6 @@ constexpr int DFT_SCRATCH_BYTES = 2 * 4 * 32 * 32 * 4;   // inverse epilogue ove
 enum DftEpilogue : int { EPI_STFT = 0, EPI_ISTFT = 1, EPI_RAW = 2 };
 
 constexpr int DFT_SMEM_LIMIT = 232448;   // 227 KB opt-in shared memory per CTA on sm_100
-
-template <int BK, int EPI>
-struct DftCfg {
-  static_assert(BK == 16 || BK == 32 || BK == 64, "K block is 16 (SWIZZLE_32B), 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
-  static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int A_BYTES = DFT_TILE_M * ROW_BYTES;     // one split of the basis tile
-  static constexpr int B_BYTES = DFT_TILE_N * ROW_BYTES;     // one split of the signal tile
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int SCRATCH_BYTES = (EPI == 1) ? DFT_SCRATCH_BYTES : 0;   // only the inverse epilogue exchanges through smem
-  static constexpr int STAGES = (DFT_SMEM_LIMIT - 1024 - 256 - SCRATCH_BYTES) / STAGE_BYTES;   // 9/8, 4, 2
-  static constexpr int K_BLOCKS = DFT_K / BK;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + SCRATCH_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers/tmem slot + alignment slack
-  static_assert(STAGES >= 2 && (2 * STAGES + 5) * 8 <= 256, "barrier block overflow");
-};
 
 struct DftParams {
   int num_signals;   // S
@@ -205,138 +192,10 @@ __device__ __forceinline__ void dft_epilogue_tile(const DftParams& p, int s, int
   }
 }
 
-template <int BK, int EPI>
-__global__ void __launch_bounds__(DFT_THREADS, 1)
-dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DftParams p) {
-  using Cfg = DftCfg<BK, EPI>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* scratch = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
-  const uint32_t bar_base = smem_base + Cfg::BAR_OFFSET;
-  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::BAR_OFFSET + 8 * (2 * Cfg::STAGES + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
-    }
-    fence_mbar_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m = tile % DFT_M_TILES;
-        const int rest = tile / DFT_M_TILES;
-        const int nt = rest % p.n_tiles;
-        const int s = rest / p.n_tiles;
-        for (int kb = 0; kb < Cfg::K_BLOCKS; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
-          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          tma_load_2d(&tmA, full_bar(stage), st, kb * BK, m * DFT_TILE_M);
-          tma_load_2d(&tmA, full_bar(stage), st + Cfg::A_BYTES, kb * BK, DFT_ROWS + m * DFT_TILE_M);
-          tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES, kb * BK, nt * DFT_TILE_N, s);
-          tma_load_3d(&tmB, full_bar(stage), st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kb * BK, nt * DFT_TILE_N, p.lo_offset + s);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(DFT_TILE_M, DFT_TILE_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 2);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * DFT_TILE_N);
-        for (int kb = 0; kb < Cfg::K_BLOCKS; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.err_flag, 3);
-          tcgen05_fence_after();
-          const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint64_t a_hi = umma_smem_desc(st, Cfg::ROW_BYTES);
-          const uint64_t a_lo = umma_smem_desc(st + Cfg::A_BYTES, Cfg::ROW_BYTES);
-          const uint64_t b_hi = umma_smem_desc(st + 2 * Cfg::A_BYTES, Cfg::ROW_BYTES);
-          const uint64_t b_lo = umma_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::ROW_BYTES);
-#pragma unroll
-          for (int k16 = 0; k16 < BK / 16; ++k16) {
-            const uint64_t adv = (uint64_t)(k16 * 2);   // 32 bytes along K inside the swizzle row, >> 4
-            umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, (kb | k16) != 0 ? 1u : 0u);
-            umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-          }
-          umma_commit(empty_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================================== epilogue ==========================================
-    const int q = warp & 3;   // TMEM lane group owned by this warp
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m = tile % DFT_M_TILES;
-      const int rest = tile / DFT_M_TILES;
-      const int nt = rest % p.n_tiles;
-      const int s = rest / p.n_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 4);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DFT_TILE_N);
-      dft_epilogue_tile<EPI>(p, s, nt, m, taddr, scratch, q, lane, [&]() { mbar_arrive(tempty_bar(acc)); });
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// CTA-pair version (cta_group::2): one 256 x 256 output tile per pair of SMs.
+// CTA pairs (cta_group::2): one 256 x 256 output tile per pair of SMs.
 //
-// With cta_group::1 every MMA re-reads its A (128 x 16) and B (256 x 16) tiles from the SM's own shared memory
+// With cta_group::1 (round 1's first kernel, since removed) every MMA re-reads its A (128 x 16) and B (256 x 16) tiles from the SM's own shared memory
 // and TMA writes 2A + 2B per K step into the same shared memory: ~158 B/clk against the 128 B/clk the shared
 // memory can move, which caps the tensor pipe at ~81 % (ncu measured 78-83 %).  A CTA pair splits the B rows
 // (frames) between the two SMs, so each SM stages and reads only half of B: ~104 B/clk, below the limit.

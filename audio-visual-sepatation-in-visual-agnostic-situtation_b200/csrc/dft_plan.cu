@@ -15,6 +15,7 @@ namespace avsep {
 // ---------------------------------------------------------------------------------------------
 // staging kernels
 // ---------------------------------------------------------------------------------------------
+// Staging of the PLAIN forward GEMM (the in-library cross-check of the folded kernels):
 // wave [S, L] fp32 -> reflect-padded (n_fft/2 each side, librosa center=True) bf16 hi/lo rows of
 // length Lpad.  Frame t of signal s is then the 1024-sample window starting at 256 t, which the
 // GEMM reads directly through an overlapping-row TMA descriptor (row stride 256 elements).
@@ -52,90 +53,14 @@ __global__ void __launch_bounds__(256) wave_split_kernel(const float* __restrict
   *reinterpret_cast<uint4*>(out + lo_stride + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// Folded operand of the forward transform (dft_fold.cuh): for every frame t and n < 512
-//   E[n] = x[n] + x[1022 - n],  O[n] = x[n] - x[1022 - n]   (E[0] = x[0], E[511] = x[511], O[0] = O[511] = 0)
-// with x the reflect-padded frame, written as bf16 hi/lo planes [kind(E,O)][split][S_cap][T][512].
-constexpr int FOLD_STAGE_FRAMES = 4;                       // frames per CTA of the staging kernel
-constexpr int FOLD_STAGE_SEG = AVSEP_HOP * (FOLD_STAGE_FRAMES - 1) + 1024;   // padded samples the CTA touches (1792)
-// The mirrored term x[1022 - n] is read from a REVERSED copy of the segment so that both terms are ascending,
-// 16-byte aligned float4 reads: rev[j] = seg[FOLD_STAGE_REV - 1 - j]  =>  frame fi: x[1022 - n] = rev[c_fi + n],
-// c_fi = FOLD_STAGE_REV - 1023 - 256 fi; FOLD_STAGE_REV = 1795 makes every c_fi a multiple of 4.
-constexpr int FOLD_STAGE_REV = 1795;
-
-__global__ void __launch_bounds__(256) wave_fold_kernel(const float* __restrict__ wave, int S, int L, int T, size_t plane_stride,
-                                                        __nv_bfloat16* __restrict__ out, int mix_B, int mix_N, int sig_base) {
-  __shared__ __align__(16) float seg[FOLD_STAGE_SEG];
-  __shared__ __align__(16) float rev[FOLD_STAGE_REV + 1];
-  const int t0 = blockIdx.x * FOLD_STAGE_FRAMES;
-  const int s_local = blockIdx.y;                 // slot in the staging planes
-  const int s = s_local + sig_base;               // signal in the caller's batch
-  const bool is_mix = mix_N > 0 && s < mix_B;
-  const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
-  const size_t src_stride = (size_t)mix_B * L;
-  // 1. the reflect-padded segment covering the CTA's frames, read once (coalesced), mixture summed on the fly
-  for (int i = threadIdx.x; i < FOLD_STAGE_SEG; i += blockDim.x) {
-    int j = t0 * AVSEP_HOP + i - AVSEP_N_FFT / 2;
-    if (j < 0) j = -j;
-    if (j >= L) j = 2 * (L - 1) - j;
-    float x = 0.f;
-    if (j >= 0 && j < L) {
-      x = __ldg(w + j);
-      if (is_mix)
-        for (int n = 1; n < mix_N; ++n) x += __ldg(w + n * src_stride + j);
-    }
-    seg[i] = x;
-    rev[FOLD_STAGE_REV - 1 - i] = x;
-  }
-  __syncthreads();
-  // 2. one work item per thread: frame fi, 8 consecutive n  ->  four 16-byte stores (E hi, E lo, O hi, O lo)
-  const int fi = threadIdx.x >> 6;
-  const int t = t0 + fi;
-  if (t >= T) return;
-  const int n0 = (threadIdx.x & 63) * 8;
-  const float4* fa = reinterpret_cast<const float4*>(seg + fi * AVSEP_HOP + n0);
-  const float4* fb = reinterpret_cast<const float4*>(rev + (FOLD_STAGE_REV - 1023 - AVSEP_HOP * fi) + n0);
-  const float4 a0 = fa[0], a1 = fa[1], b0 = fb[0], b1 = fb[1];
-  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  __align__(16) __nv_bfloat16 v[4][8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int n = n0 + e;
-    const bool paired = n >= 1 && n <= AVSEP_N_FFT / 2 - 1;
-    const float E = paired ? a[e] + b[e] : a[e];
-    const float O = paired ? a[e] - b[e] : 0.f;
-    split_bf16(E, v[0][e], v[1][e]);
-    split_bf16(O, v[2][e], v[3][e]);
-  }
-  const size_t o = ((size_t)s_local * T + t) * FOLD_K + n0;
-#pragma unroll
-  for (int pl = 0; pl < 4; ++pl) *reinterpret_cast<uint4*>(out + pl * plane_stride + o) = *reinterpret_cast<const uint4*>(v[pl]);
-}
-
-// Fallback when the overlapping-row descriptor is not available: materialise frames [S, T, 1024].
-__global__ void wave_frames_kernel(const float* __restrict__ wave, int S, int L, int T, size_t lo_stride,
-                                   __nv_bfloat16* __restrict__ out, int mix_B, int mix_N) {
-  const int st = blockIdx.x;            // s * T + t
-  const int s = st / T, t = st % T;
-  const bool is_mix = mix_N > 0 && s < mix_B;
-  const float* w = wave + (size_t)(mix_N > 0 ? (is_mix ? s : s - mix_B) : s) * L;
-  const size_t src_stride = (size_t)mix_B * L;
-  for (int k = threadIdx.x; k < DFT_K; k += blockDim.x) {
-    int j = t * AVSEP_HOP + k - AVSEP_N_FFT / 2;
-    float x = 0.f;
-    if (k < AVSEP_N_FFT) {
-      if (j < 0) j = -j;
-      if (j >= L) j = 2 * (L - 1) - j;
-      if (j >= 0 && j < L) {
-        x = w[j];
-        if (is_mix)
-          for (int n = 1; n < mix_N; ++n) x += w[n * src_stride + j];
-      }
-    }
-    __nv_bfloat16 hi, lo;
-    split_bf16(x, hi, lo);
-    out[(size_t)st * DFT_K + k] = hi;
-    out[lo_stride + (size_t)st * DFT_K + k] = lo;
+// Mixture waveforms of a device-summed batch (dataset/music.py:127: the mixture IS the sum of its sources):
+// sources [N, B, L] -> mix [B, L].  Feeds the folded forward kernel when the mixture spectrum cannot be taken as X0 + X1
+// (N != 2, or phase / (re, im) outputs).
+__global__ void __launch_bounds__(256) mix_sum_kernel(const float* __restrict__ src, int N, size_t BL, float* __restrict__ mix) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < BL; i += (size_t)gridDim.x * blockDim.x) {
+    float x = __ldg(src + i);
+    for (int n = 1; n < N; ++n) x += __ldg(src + (size_t)n * BL + i);
+    mix[i] = x;
   }
 }
 
@@ -449,34 +374,27 @@ struct avsep_plan {
   int T = 0;
   int Lpad = 0;
   int out_len = 0;
-  int kblock = 64;
-  bool overlap_tma = true;      // frames read through the overlapping-row descriptor
-  __nv_bfloat16* basis_fwd = nullptr;   // [2][1024][1024]  (hi rows 0..1023, lo rows 1024..2047)
-  __nv_bfloat16* basis_inv = nullptr;
-  __nv_bfloat16* wave_split = nullptr;  // [2][S_cap][Lpad]   (overlap) or [2][S_cap][T][1024] (frames)
-  __nv_bfloat16* spec_split = nullptr;  // [2][S_cap][T][1024], allocated on first inverse call
-  float* inv_env = nullptr;             // [256 * (T + 3)]
-  bool fold = true;                     // forward transform through the folded (half-work) GEMM
-  int fold_prefetch = 1;
-  int fold_chunk = 0;                   // signals per staging + GEMM chunk of the folded path (0 = all at once)
-  __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
-  __nv_bfloat16* fold_split = nullptr;  // [4][S_cap][T][512]
-  CUtensorMap tm_basis_fold, tm_fold;
-  CUtensorMap tm_basis_fold32;          // the same basis with 32-column SWIZZLE_64B boxes (dft_fold3)
-  bool fused_stage = true;              // dft_fold3: E / O operand generated inside the GEMM, no staging kernel
+  // product kernels: folded forward (dft_fold3 / dft_fold3m, operand generated in the kernel) and folded inverse
+  // (idft_fold2); the plain 1024 x 1024 CTA-pair GEMM of dft_gemm.cuh is kept as their in-library cross-check
+  bool fold = true;                     // forward transform through the folded kernels
   bool mix_linear = true;               // two-source device-summed mixtures: |X0 + X1| from the two source transforms (dft_fold3m)
-  int fold3_sets = 2;                   // producer groups of dft_fold3 (1: all warps on every K step, 2: alternate K steps)
+  bool inverse_fold = true;             // inverse transform through the folded kernel
+  int generation = 0;                   // bumped by every avsep_plan_set_*: captured CUDA graphs of a step are keyed on it
+  __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
+  __nv_bfloat16* basis_ifold = nullptr; // [4 = kind * 2 + split][512 rows in CTA-group order][512 bins]
+  __nv_bfloat16* basis_fwd = nullptr;   // plain: [2][1024][1024]  (hi rows 0..1023, lo rows 1024..2047)
+  __nv_bfloat16* basis_inv = nullptr;
+  __nv_bfloat16* wave_split = nullptr;  // plain forward operand [2][S_cap][Lpad], allocated on first use
+  __nv_bfloat16* spec_split = nullptr;  // inverse operand [2][S_cap][T][1024], allocated on first inverse call
+  float* wave_mix = nullptr;            // [mix_cap] mixture waveforms summed on the device (allocated on first use)
+  size_t mix_cap = 0;
+  float* inv_env = nullptr;             // [256 * (T + 3)]
   const float* last_wave = nullptr;     // arguments of the last forward transform, for avsep_debug_gemm_only
   int last_mix_B = 0, last_mix_N = 0;
   int* err_flag = nullptr;
-  CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave, tm_spec;
-  CUtensorMap tm_wave2, tm_spec2;       // same tensors, 128-frame boxes for the CTA-pair kernel
-  bool two_cta = true;                  // cta_group::2 GEMM (one 256 x 256 tile per SM pair)
-  bool tm_spec_valid = false;
-  int generation = 0;                   // bumped by every avsep_plan_set_*: captured CUDA graphs of a step are keyed on it
-  bool inverse_fold = true;             // inverse transform through the folded (half-work) GEMM (idft_fold.cuh)
-  __nv_bfloat16* basis_ifold = nullptr; // [4 = kind * 2 + split][512 rows in CTA-group order][512 bins]
-  CUtensorMap tm_basis_ifold, tm_spec_ifold;
+  CUtensorMap tm_basis_fold32, tm_basis_ifold, tm_spec_ifold;      // folded kernels
+  CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave2, tm_spec2;      // plain CTA-pair GEMM (128-frame boxes)
+  bool tm_wave_valid = false;
   size_t workspace = 0;
 };
 
@@ -495,57 +413,35 @@ static int encode_map(CUtensorMap* tm, void* base, int rank, const cuuint64_t* d
   return AVSEP_OK;
 }
 
+constexpr int PLAIN_BK = 64;            // K block of the plain GEMM (SWIZZLE_128B)
+
 static int build_maps(avsep_plan* pl) {
-  const int bk = pl->kblock;
   {
     cuuint64_t dims[2] = {(cuuint64_t)DFT_K, (cuuint64_t)(2 * DFT_ROWS)};
     cuuint64_t strides[1] = {(cuuint64_t)DFT_K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_M};
-    int rc = encode_map(&pl->tm_basis_fwd, pl->basis_fwd, 2, dims, strides, box, bk);
+    cuuint32_t box[2] = {(cuuint32_t)PLAIN_BK, (cuuint32_t)DFT_TILE_M};
+    int rc = encode_map(&pl->tm_basis_fwd, pl->basis_fwd, 2, dims, strides, box, PLAIN_BK);
     if (rc) return rc;
-    rc = encode_map(&pl->tm_basis_inv, pl->basis_inv, 2, dims, strides, box, bk);
+    rc = encode_map(&pl->tm_basis_inv, pl->basis_inv, 2, dims, strides, box, PLAIN_BK);
+    if (rc) return rc;
+  }
+  if (pl->wave_split) {
+    // frame t of a signal = 1024 staged samples at offset 256 t: overlapping rows (row stride 512 B), no frame materialisation
+    cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
+    cuuint64_t strides[2] = {(cuuint64_t)AVSEP_HOP * 2, (cuuint64_t)pl->Lpad * 2};
+    cuuint32_t box2[3] = {(cuuint32_t)PLAIN_BK, (cuuint32_t)(DFT_TILE_N / 2), 1};
+    int rc = encode_map(&pl->tm_wave2, pl->wave_split, 3, dims, strides, box2, PLAIN_BK);
+    if (rc) return rc;
+    pl->tm_wave_valid = true;
+  }
+  {
+    cuuint64_t dimsA[2] = {(cuuint64_t)FOLD_K, (cuuint64_t)(4 * FOLD_BINS)};
+    cuuint64_t stridesA[1] = {(cuuint64_t)FOLD_K * 2};
+    cuuint32_t boxA32[2] = {(cuuint32_t)Fold3Cfg::BK, (cuuint32_t)FOLD_TILE_M};
+    int rc = encode_map(&pl->tm_basis_fold32, pl->basis_fold, 2, dimsA, stridesA, boxA32, Fold3Cfg::BK);
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
-    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_N, 1};
-    int rc = AVSEP_ERR_CUDA;
-    if (pl->overlap_tma) {
-      cuuint64_t strides[2] = {(cuuint64_t)AVSEP_HOP * 2, (cuuint64_t)pl->Lpad * 2};
-      rc = encode_map(&pl->tm_wave, pl->wave_split, 3, dims, strides, box, bk);
-      if (rc) pl->overlap_tma = false;   // driver rejected overlapping rows: materialise frames instead
-    }
-    if (!pl->overlap_tma) {
-      cuuint64_t strides[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
-      rc = encode_map(&pl->tm_wave, pl->wave_split, 3, dims, strides, box, bk);
-      if (rc) return rc;
-    }
-    {
-      cuuint32_t box2[3] = {(cuuint32_t)bk, (cuuint32_t)(DFT_TILE_N / 2), 1};
-      cuuint64_t strides_ov[2] = {(cuuint64_t)AVSEP_HOP * 2, (cuuint64_t)pl->Lpad * 2};
-      cuuint64_t strides_fr[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
-      rc = encode_map(&pl->tm_wave2, pl->wave_split, 3, dims, pl->overlap_tma ? strides_ov : strides_fr, box2, bk);
-      if (rc) return rc;
-    }
-  }
-  if (pl->basis_fold && pl->fold_split) {
-    cuuint64_t dimsA[2] = {(cuuint64_t)FOLD_K, (cuuint64_t)(4 * FOLD_BINS)};
-    cuuint64_t stridesA[1] = {(cuuint64_t)FOLD_K * 2};
-    cuuint32_t boxA[2] = {(cuuint32_t)std::min(bk, 64), (cuuint32_t)FOLD_TILE_M};
-    const int fbk = bk == 16 ? 32 : bk;                     // the folded kernel has BK = 32 / 64 variants only
-    boxA[0] = (cuuint32_t)fbk;
-    int rc = encode_map(&pl->tm_basis_fold, pl->basis_fold, 2, dimsA, stridesA, boxA, fbk);
-    if (rc) return rc;
-    cuuint32_t boxA32[2] = {(cuuint32_t)Fold3Cfg::BK, (cuuint32_t)FOLD_TILE_M};
-    rc = encode_map(&pl->tm_basis_fold32, pl->basis_fold, 2, dimsA, stridesA, boxA32, Fold3Cfg::BK);
-    if (rc) return rc;
-    cuuint64_t dimsB[3] = {(cuuint64_t)FOLD_K, (cuuint64_t)pl->T, (cuuint64_t)(4 * pl->max_signals)};
-    cuuint64_t stridesB[2] = {(cuuint64_t)FOLD_K * 2, (cuuint64_t)pl->T * FOLD_K * 2};
-    cuuint32_t boxB[3] = {(cuuint32_t)fbk, (cuuint32_t)FOLD_TILE_N, 1};
-    rc = encode_map(&pl->tm_fold, pl->fold_split, 3, dimsB, stridesB, boxB, fbk);
-    if (rc) return rc;
-  }
-  if (pl->basis_ifold) {
     cuuint64_t dimsA[2] = {(cuuint64_t)IFOLD_K, (cuuint64_t)(4 * IFOLD_ROWS)};
     cuuint64_t stridesA[1] = {(cuuint64_t)IFOLD_K * 2};
     cuuint32_t boxA[2] = {(cuuint32_t)IFoldCfg::BK, 128};
@@ -555,16 +451,12 @@ static int build_maps(avsep_plan* pl) {
   if (pl->spec_split) {
     cuuint64_t dims[3] = {(cuuint64_t)DFT_K, (cuuint64_t)pl->T, (cuuint64_t)(2 * pl->max_signals)};
     cuuint64_t strides[2] = {(cuuint64_t)DFT_K * 2, (cuuint64_t)pl->T * DFT_K * 2};
-    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)DFT_TILE_N, 1};
-    int rc = encode_map(&pl->tm_spec, pl->spec_split, 3, dims, strides, box, bk);
-    if (rc) return rc;
-    cuuint32_t box2[3] = {(cuuint32_t)bk, (cuuint32_t)(DFT_TILE_N / 2), 1};
-    rc = encode_map(&pl->tm_spec2, pl->spec_split, 3, dims, strides, box2, bk);
+    cuuint32_t box2[3] = {(cuuint32_t)PLAIN_BK, (cuuint32_t)(DFT_TILE_N / 2), 1};
+    int rc = encode_map(&pl->tm_spec2, pl->spec_split, 3, dims, strides, box2, PLAIN_BK);
     if (rc) return rc;
     cuuint32_t box3[3] = {(cuuint32_t)IFoldCfg::BK, (cuuint32_t)(IFOLD_TILE_N / 2), 1};
     rc = encode_map(&pl->tm_spec_ifold, pl->spec_split, 3, dims, strides, box3, IFoldCfg::BK);
     if (rc) return rc;
-    pl->tm_spec_valid = true;
   }
   return AVSEP_OK;
 }
@@ -673,106 +565,41 @@ static int launch_ifold(avsep_plan* pl, int S, float* wav_dev, cudaStream_t stre
   return AVSEP_OK;
 }
 
-template <int NG>
-static int launch_fold3(avsep_plan* pl, const FoldParams& prm, int grid2, cudaStream_t stream) {
-  auto kern = dft_fold3_fwd_kernel<NG>;
+// folded forward transform of S signals, E / O operand generated in the kernel from the fp32 waveforms
+static int launch_fold3(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
+  const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
+  const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
+  const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+  if (grid2 <= 0) return AVSEP_OK;
+  auto kern = dft_fold3_fwd_kernel<2>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
   kern<<<grid2, FOLD3_THREADS, Fold3Cfg::SMEM_BYTES, stream>>>(pl->tm_basis_fold32, prm);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
 
-// mixtures summed on the device (mix_N > 0) keep the staged path: wave_fold_kernel sums the sources while staging
-static bool use_fold3(const avsep_plan* pl, int mix_N = 0) { return pl->fold && pl->two_cta && pl->fused_stage && mix_N == 0; }
-
 // forward transform of a device-summed two-source mixture batch (see dft_fold3m in dft_fold.cuh)
-template <int NG>
 static int launch_fold3m(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
   const int n_tiles = ceil_div(prm.T, FOLD3M_TILE_N);
   const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
   const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
   if (grid2 <= 0) return AVSEP_OK;
-  auto kern = dft_fold3m_fwd_kernel<NG>;
+  auto kern = dft_fold3m_fwd_kernel<2>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
   kern<<<grid2, FOLD3_THREADS, Fold3Cfg::SMEM_BYTES, stream>>>(pl->tm_basis_fold32, prm);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
 
-static int launch_fold(avsep_plan* pl, FoldParams prm, cudaStream_t stream) {
-  if (prm.wave != nullptr) {
-    const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
-    const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
-    const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
-    if (grid2 <= 0) return AVSEP_OK;
-    return pl->fold3_sets == 2 ? launch_fold3<2>(pl, prm, grid2, stream) : launch_fold3<1>(pl, prm, grid2, stream);
-  }
-  if (pl->two_cta) {
-    const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
-    const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
-    const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
-    if (grid2 <= 0) return AVSEP_OK;
-    if (pl->kblock == 64) {
-      auto kern = dft_fold2_fwd_kernel<64>;
-      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold2Cfg<64>::SMEM_BYTES));
-      kern<<<grid2, FOLD_THREADS, Fold2Cfg<64>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
-    } else {
-      auto kern = dft_fold2_fwd_kernel<32>;
-      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold2Cfg<32>::SMEM_BYTES));
-      kern<<<grid2, FOLD_THREADS, Fold2Cfg<32>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
-    }
-    AVSEP_LAUNCH_CHECK();
-    return AVSEP_OK;
-  }
-  const int grid = std::min(prm.total_tiles, sm_count());
-  if (grid <= 0) return AVSEP_OK;
-  if (pl->kblock == 64) {
-    auto kern = dft_fold_fwd_kernel<64>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FoldCfg<64>::SMEM_BYTES));
-    kern<<<grid, FOLD_THREADS, FoldCfg<64>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
-  } else {
-    auto kern = dft_fold_fwd_kernel<32>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FoldCfg<32>::SMEM_BYTES));
-    kern<<<grid, FOLD_THREADS, FoldCfg<32>::SMEM_BYTES, stream>>>(pl->tm_basis_fold, pl->tm_fold, prm);
-  }
-  AVSEP_LAUNCH_CHECK();
-  return AVSEP_OK;
-}
-
+// the plain 1024 x 1024 CTA-pair GEMM (cross-check of the folded kernels, raw-accumulator debug hook)
 template <int EPI>
-static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB, DftParams prm, cudaStream_t stream,
-                       const CUtensorMap* tmB2 = nullptr) {
-  if (pl->two_cta && tmB2 != nullptr && pl->kblock != 16) {
-    const int pair_tiles = prm.total_tiles / 2;
-    const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
-    if (grid2 <= 0) return AVSEP_OK;
-    if (pl->kblock == 64) {
-      auto kern = dft_gemm2_kernel<64, EPI>;
-      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dft2Cfg<64, EPI>::SMEM_BYTES));
-      kern<<<grid2, DFT_THREADS, Dft2Cfg<64, EPI>::SMEM_BYTES, stream>>>(tmA, *tmB2, prm);
-    } else {
-      auto kern = dft_gemm2_kernel<32, EPI>;
-      AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dft2Cfg<32, EPI>::SMEM_BYTES));
-      kern<<<grid2, DFT_THREADS, Dft2Cfg<32, EPI>::SMEM_BYTES, stream>>>(tmA, *tmB2, prm);
-    }
-    AVSEP_LAUNCH_CHECK();
-    return AVSEP_OK;
-  }
-  const int grid = std::min(prm.total_tiles, sm_count());
-  if (grid <= 0) return AVSEP_OK;
-  if (pl->kblock == 64) {
-    auto kern = dft_gemm_kernel<64, EPI>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<64, EPI>::SMEM_BYTES));
-    kern<<<grid, DFT_THREADS, DftCfg<64, EPI>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
-  } else if (pl->kblock == 16) {
-    auto kern = dft_gemm_kernel<16, EPI>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<16, EPI>::SMEM_BYTES));
-    kern<<<grid, DFT_THREADS, DftCfg<16, EPI>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
-  } else {
-    auto kern = dft_gemm_kernel<32, EPI>;
-    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DftCfg<32, EPI>::SMEM_BYTES));
-    kern<<<grid, DFT_THREADS, DftCfg<32, EPI>::SMEM_BYTES, stream>>>(tmA, tmB, prm);
-  }
+static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB2, DftParams prm, cudaStream_t stream) {
+  const int pair_tiles = prm.total_tiles / 2;
+  const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+  if (grid2 <= 0) return AVSEP_OK;
+  auto kern = dft_gemm2_kernel<PLAIN_BK, EPI>;
+  AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dft2Cfg<PLAIN_BK, EPI>::SMEM_BYTES));
+  kern<<<grid2, DFT_THREADS, Dft2Cfg<PLAIN_BK, EPI>::SMEM_BYTES, stream>>>(tmA, tmB2, prm);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
@@ -791,23 +618,18 @@ static DftParams base_params(const avsep_plan* pl, int S) {
   return prm;
 }
 
+// operand of the plain forward GEMM (allocated on first use: the product path never needs it)
 static int stage_waves(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B = 0, int mix_N = 0) {
-  if (pl->overlap_tma) {
-    const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
-    dim3 grid(ceil_div(pl->Lpad, 256 * 8), S);
-    wave_split_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->Lpad, lo_stride, pl->wave_split, mix_B, mix_N);
-  } else {
-    const size_t lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
-    wave_frames_kernel<<<S * pl->T, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, lo_stride, pl->wave_split, mix_B, mix_N);
+  if (!pl->wave_split) {
+    const size_t bytes = (size_t)2 * pl->max_signals * pl->Lpad * sizeof(__nv_bfloat16);
+    AVSEP_CUDA(cudaMalloc(&pl->wave_split, bytes));
+    pl->workspace += bytes;
+    int rc = build_maps(pl);
+    if (rc) return rc;
   }
-  AVSEP_LAUNCH_CHECK();
-  return AVSEP_OK;
-}
-
-static int stage_fold(avsep_plan* pl, const float* wave_dev, int S, cudaStream_t stream, int mix_B, int mix_N, int sig_base) {
-  const size_t plane = (size_t)pl->max_signals * pl->T * FOLD_K;
-  dim3 grid(ceil_div(pl->T, FOLD_STAGE_FRAMES), S);
-  wave_fold_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->T, plane, pl->fold_split, mix_B, mix_N, sig_base);
+  const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
+  dim3 grid(ceil_div(pl->Lpad, 256 * 8), S);
+  wave_split_kernel<<<grid, 256, 0, stream>>>(wave_dev, S, pl->wave_len, pl->Lpad, lo_stride, pl->wave_split, mix_B, mix_N);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
@@ -841,11 +663,6 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
   pl->T = 1 + wave_len / AVSEP_HOP;
   pl->Lpad = AVSEP_HOP * (pl->T + 4);
   pl->out_len = AVSEP_HOP * (pl->T - 1);
-  const char* env_bk = getenv("AVSEP_DFT_KBLOCK");
-  pl->kblock = env_bk ? atoi(env_bk) : 64;     // 64 (SWIZZLE_128B, 2 x 96 KB stages) measured fastest on B200
-  if (pl->kblock != 16 && pl->kblock != 32 && pl->kblock != 64) pl->kblock = 64;
-  const char* env_ov = getenv("AVSEP_DFT_NO_OVERLAP_TMA");
-  pl->overlap_tma = !(env_ov && atoi(env_ov) != 0);
 
   std::vector<uint16_t> fwd, inv;
   fill_basis(fwd, inv);
@@ -882,27 +699,11 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
   PLAN_CUDA(cudaMemset(pl->err_flag, 0, sizeof(int)));
 
   {
-    const char* env_fold = getenv("AVSEP_DFT_FOLD");
-    pl->fold = !(env_fold && atoi(env_fold) == 0);
-    const char* env_2 = getenv("AVSEP_DFT_2CTA");
-    pl->two_cta = !(env_2 && atoi(env_2) == 0);
-    const char* env_ch = getenv("AVSEP_DFT_FOLD_CHUNK");
-    pl->fold_chunk = env_ch ? atoi(env_ch) : 0;     // measured: chunking is neutral (0.584 ms/step either way), so one launch pair
-    const char* env_fs = getenv("AVSEP_DFT_FUSED_STAGE");
-    pl->fused_stage = !(env_fs && atoi(env_fs) == 0);
-    const char* env_ml = getenv("AVSEP_DFT_MIX_LINEAR");
-    pl->mix_linear = !(env_ml && atoi(env_ml) == 0);
-    const char* env_pw = getenv("AVSEP_DFT_FOLD3_GROUPS");
-    pl->fold3_sets = (env_pw && atoi(env_pw) == 1) ? 1 : 2;
-    const char* env_pf = getenv("AVSEP_DFT_FOLD_PREFETCH");
-    pl->fold_prefetch = !(env_pf && atoi(env_pf) == 0);
     std::vector<uint16_t> fb;
     fill_basis_fold(fb);
     PLAN_CUDA(cudaMalloc(&pl->basis_fold, fb.size() * 2));
     PLAN_CUDA(cudaMemcpy(pl->basis_fold, fb.data(), fb.size() * 2, cudaMemcpyHostToDevice));
-    const size_t fold_elems = (size_t)4 * max_signals * pl->T * FOLD_K;
-    PLAN_CUDA(cudaMalloc(&pl->fold_split, fold_elems * sizeof(__nv_bfloat16)));
-    pl->workspace += fb.size() * 2 + fold_elems * sizeof(__nv_bfloat16);
+    pl->workspace += fb.size() * 2;
   }
   {
     std::vector<uint16_t> ib;
@@ -911,26 +712,8 @@ int avsep_plan_create(avsep_plan** plan, int max_signals, int wave_len) {
     PLAN_CUDA(cudaMemcpy(pl->basis_ifold, ib.data(), ib.size() * 2, cudaMemcpyHostToDevice));
     pl->workspace += ib.size() * 2;
   }
-  // staging buffer: large enough for either layout decision below
-  {
-    const size_t ov = (size_t)2 * max_signals * pl->Lpad;
-    const size_t fr = (size_t)2 * max_signals * pl->T * DFT_K;
-    const size_t elems = pl->overlap_tma ? ov : fr;
-    PLAN_CUDA(cudaMalloc(&pl->wave_split, elems * sizeof(__nv_bfloat16)));
-    pl->workspace += elems * sizeof(__nv_bfloat16);
-    const bool wanted_overlap = pl->overlap_tma;
-    rc = build_maps(pl);
-    if (rc) return fail(rc);
-    if (wanted_overlap && !pl->overlap_tma) {
-      // descriptor fell back to materialised frames: regrow the buffer and re-encode
-      cudaFree(pl->wave_split);
-      pl->workspace -= elems * sizeof(__nv_bfloat16);
-      PLAN_CUDA(cudaMalloc(&pl->wave_split, fr * sizeof(__nv_bfloat16)));
-      pl->workspace += fr * sizeof(__nv_bfloat16);
-      rc = build_maps(pl);
-      if (rc) return fail(rc);
-    }
-  }
+  rc = build_maps(pl);
+  if (rc) return fail(rc);
 #undef PLAN_CUDA
   *plan = pl;
   return AVSEP_OK;
@@ -945,7 +728,7 @@ int avsep_plan_destroy(avsep_plan* pl) {
   cudaFree(pl->inv_env);
   cudaFree(pl->basis_fold);
   cudaFree(pl->basis_ifold);
-  cudaFree(pl->fold_split);
+  cudaFree(pl->wave_mix);
   cudaFree(pl->err_flag);
   delete pl;
   return AVSEP_OK;
@@ -958,17 +741,7 @@ size_t avsep_plan_workspace_bytes(const avsep_plan* pl) { return pl ? pl->worksp
 int avsep_plan_set_fold(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fold: plan is null");
   ++pl->generation;
-  pl->fold = (enable & 1) != 0;
-  pl->fold_prefetch = (enable & 2) ? 0 : 1;          // bit 1 set: folded GEMM without the L2 prefetch (A/B timing)
-  return AVSEP_OK;
-}
-
-int avsep_plan_set_fused_stage(avsep_plan* pl, int enable, int groups) {
-  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_fused_stage: plan is null");
-  ++pl->generation;
-  AVSEP_REQUIRE(groups >= 0 && groups <= 2, "avsep_plan_set_fused_stage: groups must be 0 (keep), 1 or 2 (got %d)", groups);
-  pl->fused_stage = enable != 0;
-  if (groups) pl->fold3_sets = groups;
+  pl->fold = enable != 0;
   return AVSEP_OK;
 }
 
@@ -986,26 +759,22 @@ int avsep_plan_set_inverse_fold(avsep_plan* pl, int enable) {
   return AVSEP_OK;
 }
 
-int avsep_plan_set_two_cta(avsep_plan* pl, int enable) {
-  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_two_cta: plan is null");
-  ++pl->generation;
-  pl->two_cta = enable != 0;
-  return AVSEP_OK;
-}
-
-int avsep_plan_set_kblock(avsep_plan* pl, int kblock) {
-  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_kblock: plan is null");
-  ++pl->generation;
-  AVSEP_REQUIRE(kblock == 16 || kblock == 32 || kblock == 64, "avsep_plan_set_kblock: kblock must be 16, 32 or 64 (got %d)", kblock);
-  AVSEP_CUDA(cudaDeviceSynchronize());
-  pl->kblock = kblock;
-  return build_maps(pl);
-}
-
 }  // extern "C"
 
 namespace avsep {
 int plan_generation(const avsep_plan* pl) { return pl ? pl->generation : 0; }
+
+static FoldParams fold_params(const avsep_plan* pl, int num_signals, float* mag_dev) {
+  FoldParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.num_signals = num_signals;
+  fp.T = pl->T;
+  fp.mag = mag_dev;
+  fp.prefetch = 1;
+  fp.err_flag = pl->err_flag;
+  fp.L = pl->wave_len;
+  return fp;
+}
 
 int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, float* phase_dev, float* re_dev, float* im_dev,
               int reim_count, void* stream_, int mix_B, int mix_N) {
@@ -1018,50 +787,36 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   pl->last_wave = wave_dev;
   pl->last_mix_B = mix_B;
   pl->last_mix_N = mix_N;
-  if (use_fold3(pl) && pl->mix_linear && mix_N == 2 && S == 3 * mix_B && !phase_dev && !re_dev) {
+  if (pl->fold && pl->mix_linear && mix_N == 2 && S == 3 * mix_B && !phase_dev && !re_dev) {
     // magnitudes of [mixture | source 0 | source 1] from TWO transforms: the mixture is the sum of its sources
-    FoldParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.num_signals = mix_B;
-    fp.T = pl->T;
-    fp.mag = mag_dev;
-    fp.prefetch = pl->fold_prefetch;
-    fp.err_flag = pl->err_flag;
+    FoldParams fp = fold_params(pl, mix_B, mag_dev);
     fp.wave = wave_dev;
-    fp.L = pl->wave_len;
-    return pl->fold3_sets == 2 ? launch_fold3m<2>(pl, fp, stream) : launch_fold3m<1>(pl, fp, stream);
+    return launch_fold3m(pl, fp, stream);
   }
   if (pl->fold) {
-    // Optional chunking (AVSEP_DFT_FOLD_CHUNK = signals per chunk, e.g. 74 = two rounds of pair tiles): the staged
-    // E / O planes of a chunk (1 MB per signal) are then consumed by the GEMM right after they are written and
-    // the slots are reused, so they can stay in the 126 MB L2.  Measured neutral on B200, hence off by default.
-    const int chunk = pl->fold_chunk > 0 ? pl->fold_chunk : S;
-    for (int c0 = 0; c0 < S; c0 += chunk) {
-      const int n = std::min(chunk, S - c0);
-      const bool fused = use_fold3(pl, mix_N);
-      int rcf = fused ? AVSEP_OK : stage_fold(pl, wave_dev, n, stream, mix_B, mix_N, c0);
-      if (rcf) return rcf;
-      FoldParams fp;
-      memset(&fp, 0, sizeof(fp));
-      fp.wave = fused ? wave_dev : nullptr;            // non-null selects dft_fold3 in launch_fold
-      fp.L = pl->wave_len;
-      fp.num_signals = n;
-      fp.T = pl->T;
-      fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
-      fp.total_tiles = n * fp.n_tiles * FOLD_M_TILES;
-      fp.s_cap = pl->max_signals;
-      fp.sig_base = c0;
-      fp.mag = mag_dev;
-      fp.phase = phase_dev;
-      fp.re = re_dev;
-      fp.im = im_dev;
-      fp.reim_count = reim_count;
-      fp.prefetch = pl->fold_prefetch;
-      fp.err_flag = pl->err_flag;
-      rcf = launch_fold(pl, fp, stream);
-      if (rcf) return rcf;
+    FoldParams fp = fold_params(pl, S, mag_dev);
+    fp.wave = wave_dev;
+    fp.phase = phase_dev;
+    fp.re = re_dev;
+    fp.im = im_dev;
+    fp.reim_count = reim_count;
+    if (mix_N > 0) {
+      // `wave_dev` holds the N sources only: the mixture waveforms (signals 0..mix_B-1) are summed into a plan buffer
+      const size_t BL = (size_t)mix_B * pl->wave_len;
+      if (pl->mix_cap < BL) {
+        AVSEP_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(pl->wave_mix);
+        pl->wave_mix = nullptr;
+        AVSEP_CUDA(cudaMalloc(&pl->wave_mix, BL * sizeof(float)));
+        pl->workspace += (BL - pl->mix_cap) * sizeof(float);
+        pl->mix_cap = BL;
+      }
+      mix_sum_kernel<<<(unsigned)std::min<size_t>((BL + 255) / 256, 4096), 256, 0, stream>>>(wave_dev, mix_N, BL, pl->wave_mix);
+      AVSEP_LAUNCH_CHECK();
+      fp.wave_mix = pl->wave_mix;
+      fp.mix_B = mix_B;
     }
-    return AVSEP_OK;
+    return launch_fold3(pl, fp, stream);
   }
   int rc = stage_waves(pl, wave_dev, S, stream, mix_B, mix_N);
   if (rc) return rc;
@@ -1071,7 +826,7 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   prm.re = re_dev;
   prm.im = im_dev;
   prm.reim_count = reim_count;
-  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, stream, &pl->tm_wave2);
+  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave2, prm, stream);
 }
 }  // namespace avsep
 
@@ -1148,27 +903,32 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
   if (pl->inverse_fold) return launch_ifold(pl, B * nsig, wav_dev, stream);
   DftParams prm = base_params(pl, B * nsig);
   prm.wav = wav_dev;
-  return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, stream, &pl->tm_spec2);
+  return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec2, prm, stream);
 }
 
 int avsep_istft(avsep_plan* pl, const float* mag_dev, const float* phase_dev, int S, float* wav_dev, void* stream) {
   return avsep_separate(pl, nullptr, 0, S, mag_dev, phase_dev, nullptr, nullptr, 0, 0, 0.5f, 1, wav_dev, stream);
 }
 
+// raw accumulator of the PLAIN forward / inverse GEMM on the operands staged in the plan (forward: by a prior avsep_stft
+// with the fold switched off; inverse: by a prior avsep_separate / avsep_istft)
 int avsep_debug_raw_gemm(avsep_plan* pl, int inverse, int S, float* out_dev, void* stream_) {
   AVSEP_REQUIRE(pl && out_dev, "avsep_debug_raw_gemm: null argument");
   AVSEP_REQUIRE(S >= 1 && S <= pl->max_signals, "avsep_debug_raw_gemm: bad S");
   if (inverse) {
     int rc = ensure_spec(pl);
     if (rc) return rc;
+  } else {
+    AVSEP_REQUIRE(pl->tm_wave_valid, "avsep_debug_raw_gemm: no staged forward operand (call avsep_stft with avsep_plan_set_fold(plan, 0) first)");
   }
   DftParams prm = base_params(pl, S);
   prm.raw = out_dev;
-  return launch_gemm<EPI_RAW>(pl, inverse ? pl->tm_basis_inv : pl->tm_basis_fwd, inverse ? pl->tm_spec : pl->tm_wave, prm,
-                              (cudaStream_t)stream_, inverse ? &pl->tm_spec2 : &pl->tm_wave2);
+  return launch_gemm<EPI_RAW>(pl, inverse ? pl->tm_basis_inv : pl->tm_basis_fwd, inverse ? pl->tm_spec2 : pl->tm_wave2, prm,
+                              (cudaStream_t)stream_);
 }
 
-// product epilogues on the operands already staged in the plan (bench.py times the GEMM kernels alone with this)
+// the transform kernel alone with its product epilogue (bench.py / tools time the kernels in isolation with this):
+// inverse on the operand already staged in the plan; forward on the waveform pointer of the last avsep_stft call
 int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, void* stream_) {
   AVSEP_REQUIRE(pl && out_dev, "avsep_debug_gemm_only: null argument");
   AVSEP_REQUIRE(S >= 1 && S <= pl->max_signals, "avsep_debug_gemm_only: bad S");
@@ -1179,28 +939,21 @@ int avsep_debug_gemm_only(avsep_plan* pl, int inverse, int S, float* out_dev, vo
     AVSEP_REQUIRE(pl->T <= DFT_TILE_N, "avsep_debug_gemm_only: inverse needs T <= %d", DFT_TILE_N);
     if (pl->inverse_fold) return launch_ifold(pl, S, out_dev, (cudaStream_t)stream_);
     prm.wav = out_dev;
-    return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec, prm, (cudaStream_t)stream_, &pl->tm_spec2);
+    return launch_gemm<EPI_ISTFT>(pl, pl->tm_basis_inv, pl->tm_spec2, prm, (cudaStream_t)stream_);
   }
   if (pl->fold) {
-    FoldParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.num_signals = S;
-    fp.T = pl->T;
-    fp.n_tiles = ceil_div(pl->T, FOLD_TILE_N);
-    fp.total_tiles = S * fp.n_tiles * FOLD_M_TILES;
-    fp.s_cap = pl->max_signals;
-    fp.mag = out_dev;
-    fp.prefetch = pl->fold_prefetch;
-    fp.err_flag = pl->err_flag;
-    if (use_fold3(pl, pl->last_mix_N)) {   // no staged operand exists: the kernel reads the waveform of the last avsep_stft call
-      AVSEP_REQUIRE(pl->last_wave != nullptr, "avsep_debug_gemm_only: call avsep_stft on this plan first");
-      fp.wave = pl->last_wave;
-      fp.L = pl->wave_len;
+    AVSEP_REQUIRE(pl->last_wave != nullptr, "avsep_debug_gemm_only: call avsep_stft on this plan first");
+    FoldParams fp = fold_params(pl, S, out_dev);
+    fp.wave = pl->last_wave;
+    if (pl->last_mix_N > 0) {                       // the mixture waveforms of the last call are still in the plan buffer
+      fp.wave_mix = pl->wave_mix;
+      fp.mix_B = pl->last_mix_B;
     }
-    return launch_fold(pl, fp, (cudaStream_t)stream_);
+    return launch_fold3(pl, fp, (cudaStream_t)stream_);
   }
+  AVSEP_REQUIRE(pl->tm_wave_valid, "avsep_debug_gemm_only: no staged forward operand");
   prm.mag = out_dev;
-  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave, prm, (cudaStream_t)stream_, &pl->tm_wave2);
+  return launch_gemm<EPI_STFT>(pl, pl->tm_basis_fwd, pl->tm_wave2, prm, (cudaStream_t)stream_);
 }
 
 int avsep_debug_basis(avsep_plan* pl, int inverse, float* out_host) {
@@ -1216,23 +969,15 @@ int avsep_debug_basis(avsep_plan* pl, int inverse, float* out_host) {
 // separate "staging is wrong" from "the tensor-core pipeline is wrong"
 int avsep_debug_staged_frames(avsep_plan* pl, int s, float* out_host) {
   AVSEP_REQUIRE(pl && out_host && s >= 0 && s < pl->max_signals, "avsep_debug_staged_frames: bad argument");
+  AVSEP_REQUIRE(pl->wave_split != nullptr, "avsep_debug_staged_frames: no staged forward operand");
   AVSEP_CUDA(cudaDeviceSynchronize());
-  if (pl->overlap_tma) {
-    std::vector<uint16_t> hi(pl->Lpad), lo(pl->Lpad);
-    const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
-    AVSEP_CUDA(cudaMemcpy(hi.data(), pl->wave_split + (size_t)s * pl->Lpad, pl->Lpad * 2, cudaMemcpyDeviceToHost));
-    AVSEP_CUDA(cudaMemcpy(lo.data(), pl->wave_split + lo_stride + (size_t)s * pl->Lpad, pl->Lpad * 2, cudaMemcpyDeviceToHost));
-    for (int t = 0; t < pl->T; ++t)
-      for (int k = 0; k < DFT_K; ++k)
-        out_host[(size_t)t * DFT_K + k] = host_bf16_to_f32(hi[t * AVSEP_HOP + k]) + host_bf16_to_f32(lo[t * AVSEP_HOP + k]);
-  } else {
-    const size_t n = (size_t)pl->T * DFT_K;
-    std::vector<uint16_t> hi(n), lo(n);
-    const size_t lo_stride = (size_t)pl->max_signals * n;
-    AVSEP_CUDA(cudaMemcpy(hi.data(), pl->wave_split + (size_t)s * n, n * 2, cudaMemcpyDeviceToHost));
-    AVSEP_CUDA(cudaMemcpy(lo.data(), pl->wave_split + lo_stride + (size_t)s * n, n * 2, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) out_host[i] = host_bf16_to_f32(hi[i]) + host_bf16_to_f32(lo[i]);
-  }
+  std::vector<uint16_t> hi(pl->Lpad), lo(pl->Lpad);
+  const size_t lo_stride = (size_t)pl->max_signals * pl->Lpad;
+  AVSEP_CUDA(cudaMemcpy(hi.data(), pl->wave_split + (size_t)s * pl->Lpad, pl->Lpad * 2, cudaMemcpyDeviceToHost));
+  AVSEP_CUDA(cudaMemcpy(lo.data(), pl->wave_split + lo_stride + (size_t)s * pl->Lpad, pl->Lpad * 2, cudaMemcpyDeviceToHost));
+  for (int t = 0; t < pl->T; ++t)
+    for (int k = 0; k < DFT_K; ++k)
+      out_host[(size_t)t * DFT_K + k] = host_bf16_to_f32(hi[t * AVSEP_HOP + k]) + host_bf16_to_f32(lo[t * AVSEP_HOP + k]);
   return AVSEP_OK;
 }
 

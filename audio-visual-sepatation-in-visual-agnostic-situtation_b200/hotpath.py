@@ -196,6 +196,66 @@ def calc_metrics(batch_data, outputs, args, get_metrics: Optional[Callable] = No
 
 
 # ------------------------------------------------------------------------------------------------
+# inference.py
+# ------------------------------------------------------------------------------------------------
+def get_spec(wav, device="cuda"):
+    """inference.get_audfuncs()[1] = get_spec (inference.py:221-226): numpy wav [L] -> (amp, phase), each a CUDA tensor
+    [1, 1, 512, T]; magnitude and angle come out of the STFT kernel's epilogue."""
+    w = torch.as_tensor(np.ascontiguousarray(wav), dtype=torch.float32).to(device, non_blocking=True)
+    amp, phase = ops.stft(w.reshape(1, -1), phase=True)
+    return amp[:, None], phase[:, None]
+
+
+def prepare_inferdata(audios, frames, args):
+    """NetWrapper.prepare_inferdata (inference.py:39-52): (mag_mix [B,1,512,T], phase_mix) -> (frames, mag_mix warped to the
+    256-row log-frequency grid (+1e-10 before the warp), its log, phase_mix), in one fused kernel.  The reference's
+    vis_video calls this once per video frame on the SAME audio (inference.py:557-563); call it once and reuse the
+    result."""
+    mag_mix, phase_mix = audios
+    _, mix_w, log_mix, _, _ = ops.prepare(mag_mix, [], log_freq=True, weighted_loss=False, binary_mask=True)
+    return frames, mix_w, log_mix, phase_mix
+
+
+def recover_aud_arrays(meta, audios, mask_thres: float = 0.5):
+    """The arithmetic of inference.recover_aud (inference.py:433-491) on the GPU: un-warp the predicted masks to the
+    linear frequency axis, threshold at 0.5 (the reference hard-codes `if True:` binary masks there), mask the mixture
+    spectrogram, iSTFT.  meta['pred_masks']: list of N tensors [1,1,256,T]; audios = (mag_mix, phase_mix) [1,1,512,T].
+    Returns dict(mix_wav [L'], preds_wav list of N [L'] (numpy float64, like istft_reconstruction), pred_masks list of
+    N binary [256,T] numpy, pred_masks_linear list of N binary [512,T] numpy)."""
+    pred_masks = meta['pred_masks']
+    mag_mix, phase_mix = audios
+    N = len(pred_masks)
+    dev = pred_masks[0].device
+    wav = ops.separate(list(pred_masks), mag_mix.to(dev), phase_mix.to(dev), log_freq=True, binary_mask=True,
+                       mask_thres=mask_thres, include_mix=True)                       # [B, N+1, L']
+    lin = [(ops.warp(pred_masks[n], ops.N_BINS, warp=False) > mask_thres).float() for n in range(N)]
+    wav0 = wav[0].double().cpu().numpy()
+    return dict(mix_wav=wav0[0], preds_wav=[wav0[1 + n] for n in range(N)],
+                pred_masks=[(pred_masks[n][0, 0] > mask_thres).float().cpu().numpy() for n in range(N)],
+                pred_masks_linear=[lin[n][0, 0].cpu().numpy() for n in range(N)])
+
+
+def recover_aud(meta, audios, save_folder, write: Optional[Callable] = None, audRate: int = 11025):
+    """inference.recover_aud (inference.py:433-491): recovers the mixture and the N predicted waveforms and hands them to
+    `write(path, wav, rate)` (the reference calls soundfile.write(..., subtype='PCM_24'); soundfile / imageio are host
+    I/O outside the hot path, so the writer is injected and the spectrogram / mask JPEGs are left to the caller, who gets
+    the arrays from recover_aud_arrays).  Like the reference it rebinds meta['pred_masks'][n] to the binary numpy masks
+    and returns the list of predicted-audio paths."""
+    import os
+    out = recover_aud_arrays(meta, audios)
+    N = len(out['preds_wav'])
+    if write is not None:
+        write(os.path.join(save_folder, 'mix.wav'), out['mix_wav'], audRate)
+    aud_pths = [None for _ in range(N)]
+    for n in range(N):
+        meta['pred_masks'][n] = out['pred_masks'][n][None, None]
+        aud_pths[n] = os.path.join(save_folder, 'pred{}.wav'.format(n + 1))
+        if write is not None:
+            write(aud_pths[n], out['preds_wav'][n], audRate)
+    return aud_pths
+
+
+# ------------------------------------------------------------------------------------------------
 # long-clip separation (BASELINE.json config C4; SURVEY.md section 8(d)/(f) rank 4)
 # ------------------------------------------------------------------------------------------------
 RECON_LEN = 65280      # samples a 65535-sample window reconstructs: hop * (T - 1) = 256 * 255

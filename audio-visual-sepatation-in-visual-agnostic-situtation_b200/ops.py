@@ -89,23 +89,15 @@ class Plan:
     def workspace_bytes(self) -> int:
         return int(lib.avsep_plan_workspace_bytes(self._h))
 
-    def set_kblock(self, kblock: int) -> None:
-        check(lib.avsep_plan_set_kblock(self._h, int(kblock)), "avsep_plan_set_kblock")
-
-    def set_fused_stage(self, enable: bool, groups: int = 0) -> None:
-        check(lib.avsep_plan_set_fused_stage(self._h, int(bool(enable)), int(groups)), "avsep_plan_set_fused_stage")
-
     def set_mix_linear(self, enable: bool) -> None:
         check(lib.avsep_plan_set_mix_linear(self._h, int(bool(enable))), "avsep_plan_set_mix_linear")
-
-    def set_two_cta(self, enable: bool) -> None:
-        check(lib.avsep_plan_set_two_cta(self._h, int(bool(enable))), "avsep_plan_set_two_cta")
 
     def set_inverse_fold(self, enable: bool) -> None:
         check(lib.avsep_plan_set_inverse_fold(self._h, int(bool(enable))), "avsep_plan_set_inverse_fold")
 
     def set_fold(self, enable: bool) -> None:
-        check(lib.avsep_plan_set_fold(self._h, int(enable)), "avsep_plan_set_fold")
+        """False: forward transform through the plain 1024 x 1024 GEMM (the in-library cross-check of the folded kernels)."""
+        check(lib.avsep_plan_set_fold(self._h, int(bool(enable))), "avsep_plan_set_fold")
 
     def close(self) -> None:
         if getattr(self, "_h", None) and not getattr(self, "_borrowed", False):

@@ -111,45 +111,34 @@ int avsep_separate(avsep_plan* plan, const float* masks_dev, int N, int B,
 int avsep_istft(avsep_plan* plan, const float* mag_dev, const float* phase_dev, int S,
                 float* wav_dev, void* stream);
 
-/* Debug/test hook: raw accumulator of the forward (inverse = 0) or inverse (1) DFT GEMM for the
- * operands currently staged in the plan: out_dev [S, 1024, T] fp32, row order = basis row order. */
+/* Debug/test hook: raw accumulator of the PLAIN forward (inverse = 0) or inverse (1) DFT GEMM for the operands
+ * currently staged in the plan (forward: by avsep_stft after avsep_plan_set_fold(plan, 0)): out_dev [S, 1024, T] fp32,
+ * row order = basis row order. */
 int avsep_debug_raw_gemm(avsep_plan* plan, int inverse, int S, float* out_dev, void* stream);
-/* Same, but with the product epilogue (forward: mag [S,512,T]; inverse: wav [S, 256*(T-1)]): the GEMM
- * kernel alone on already-staged operands, so it can be timed in isolation.  With fused staging (the default) the
- * forward kernel has no staged operand: it re-reads the waveform pointer of the last avsep_stft call on this plan. */
+/* The transform kernel alone with its product epilogue (forward: mag [S,512,T]; inverse: wav [S, 256*(T-1)]), so it can be
+ * timed in isolation.  The folded forward kernel has no staged operand: it re-reads the waveform pointer of the last
+ * avsep_stft call on this plan; the inverse runs on the operand the last avsep_separate staged. */
 int avsep_debug_gemm_only(avsep_plan* plan, int inverse, int S, float* out_dev, void* stream);
 /* copies the bf16 hi/lo basis (as fp32 sums) to host: out_host [1024, 1024] */
 int avsep_debug_basis(avsep_plan* plan, int inverse, float* out_host);
 /* staged forward operand (hi + lo) of signal s as fp32 on the host: out_host [T, 1024] */
 int avsep_debug_staged_frames(avsep_plan* plan, int s, float* out_host);
-/* enable = 1 (default): the forward transform uses the folded GEMM (real-input symmetry, half the tensor work);
- * 0: the plain 1024 x 1024 DFT GEMM (also what the debug hooks above exercise). */
+/* enable = 1 (default): the forward transform runs as the folded kernels (real-input symmetry: half the tensor work;
+ * the E / O operand is generated inside the kernel from the fp32 waveform, no staging kernel, no staged planes in HBM);
+ * 0: the plain 1024 x 1024 DFT GEMM on a bf16 hi / lo staged waveform -- the in-library cross-check of the folded
+ * kernels (also what avsep_debug_raw_gemm exercises). */
 int avsep_plan_set_fold(avsep_plan* plan, int enable);
-/* enable = 1 (default): the plain DFT GEMM (inverse transform, and the forward one when fold is off) runs as CTA
- * pairs (tcgen05 cta_group::2, one 256 x 256 tile per two SMs); 0: one 128 x 256 tile per CTA. */
-int avsep_plan_set_two_cta(avsep_plan* plan, int enable);
 /* enable = 1 (default): the inverse transform of avsep_separate / avsep_istft (utils.py:101-104) runs as the FOLDED
  * GEMM (csrc/idft_fold.cuh): irfft output symmetry y[n] = P[n] + Q[n], y[1022 - n] = P[n] - Q[n] turns the
  * 1024 x 1024 contraction into two 512 x 512 ones (half the tensor work), overlap-add fused in the epilogue;
  * 0: the plain 1024 x 1024 inverse DFT GEMM (kept as the in-library cross-check of the folded kernel). */
 int avsep_plan_set_inverse_fold(avsep_plan* plan, int enable);
-/* enable = 1 (default, needs fold and two_cta): the folded GEMM builds its E / O operand inside the kernel from the
- * fp32 waveform (8 producer warps per CTA fold, split to bf16 hi / lo and write the swizzled shared-memory tiles the
- * tensor core reads), so no staging kernel runs and no staged planes cross HBM; 0: wave_fold_kernel stages the planes
- * and dft_fold2 reads them by TMA (also what runs when a mixture summed on the device has N != 2 sources or needs
- * phase / (re, im) outputs; the N = 2 magnitude-only case has its own fused kernel, see avsep_plan_set_mix_linear).
- * groups: 1 = all producer warps work on every K step, 2 = two groups alternate K steps (default, measured
- * slightly faster on B200), 0 keeps the setting. */
-int avsep_plan_set_fused_stage(avsep_plan* plan, int enable, int groups);
 /* enable = 1 (default): when a step forms the mixture on the device as the sum of its N = 2 sources
  * (avsep_step_set_mix_on_device; dataset/music.py:127 defines every training mixture that way) and only magnitudes
  * are needed (training), the mixture spectrum is taken as X0 + X1 -- the STFT is linear -- so two transforms are
  * computed instead of three (dft_fold3m).  0: the mixture waveform is summed and transformed like any other signal.
  * The two routes agree to fp32 rounding (tests/test_gpu_step.py). */
 int avsep_plan_set_mix_linear(avsep_plan* plan, int enable);
-/* selects the K-block of the GEMM pipeline: 16 (32B swizzle, 9 stages), 32 (64B swizzle, 4 stages) or
- * 64 (128B swizzle, 2 stages) */
-int avsep_plan_set_kblock(avsep_plan* plan, int kblock);
 
 /* ---- K2: log-frequency warp + derivations ------------------------------------------------- */
 /* Replaces utils.warpgrid + F.grid_sample (utils.py:12-26; main.py:61-66, 216-220): separable

@@ -1,5 +1,6 @@
 """GPU parity of the fused end-to-end steps (what bench.py times) and of the calc_metrics drop-in,
 including the SDR / SIR / SAR criterion of the north star (per clip within 0.01 dB of the oracle)."""
+import os
 import types
 
 import numpy as np
@@ -351,6 +352,38 @@ def test_long_clip_windows_vs_oracle():
     full = av.assemble_windows(out[:, 0], 65280, L_long).cpu().numpy()
     covered = min(L_long, 2 * 65280 + 65280)
     assert np.max(np.abs(full[:covered] - src[:covered])) < 1e-4
+
+
+def test_inference_dropins_vs_oracle(tmp_path):
+    """inference.py drop-ins: get_spec (:221-226), prepare_inferdata (:39-52), recover_aud (:433-491)."""
+    rng = np.random.default_rng(12)
+    src = O.synth_sources(1, 2, seed=21)[0]
+    mix = src.sum(axis=0).astype(np.float32)
+    amp, phase = av.get_spec(mix)
+    assert amp.shape == (1, 1, 512, 256) and phase.shape == (1, 1, 512, 256) and amp.is_cuda
+    amp_o, ph_o = O.stft_magphase(mix)
+    assert relerr(amp[0, 0].cpu().numpy(), amp_o) < TOL
+    args = types.SimpleNamespace(num_mix=2, device="cuda")
+    frames, mag_w, log_w, ph = av.prepare_inferdata((amp, phase), "frames-pass-through", args)
+    assert frames == "frames-pass-through" and ph is phase
+    prep = O.prepare(amp_o[None, None], [], weighted_loss=False)
+    assert relerr(mag_w.cpu().numpy(), prep["mag_mix"]) < TOL
+    loud = prep["mag_mix"] > 1e-2 * prep["mag_mix"].max()
+    assert np.max(np.abs(log_w.cpu().numpy()[loud] - prep["log_mag_mix"][loud])) < 1e-4
+    masks = [rng.random((1, 1, 256, 256)).astype(np.float32) for _ in range(2)]
+    blk = [np.repeat(np.repeat((rng.random((32, 32)) > 0.5).astype(np.float32) * 0.7 + 0.15, 8, axis=0), 8, axis=1)[None, None] for _ in range(2)]
+    meta = dict(pred_masks=[torch.from_numpy(b).cuda() for b in blk])
+    written = {}
+    pths = av.recover_aud(meta, (amp, phase), str(tmp_path), write=lambda p, w, r: written.__setitem__(os.path.basename(p), (w, r)))
+    assert [os.path.basename(p) for p in pths] == ["pred1.wav", "pred2.wav"] and set(written) == {"mix.wav", "pred1.wav", "pred2.wav"}
+    assert all(r == 11025 for _, r in written.values())
+    mix_o, pred_o, _ = O.separate(amp_o[None, None], ph_o[None, None], blk, log_freq=True, binary_mask=True)
+    s0 = np.max(np.abs(mix_o))
+    assert np.max(np.abs(written["mix.wav"][0] - mix_o[0])) / s0 < TOL
+    for n in range(2):
+        assert written[f"pred{n + 1}.wav"][0].dtype == np.float64
+        assert np.max(np.abs(written[f"pred{n + 1}.wav"][0] - pred_o[0, n])) / s0 < TOL
+        assert meta["pred_masks"][n].shape == (1, 1, 256, 256) and set(np.unique(meta["pred_masks"][n])) <= {0.0, 1.0}
 
 
 def test_full_size_c3_and_c5_properties():
