@@ -215,8 +215,150 @@ __global__ void __launch_bounds__(PREP_TX * PREP_TY, NS >= 3 ? 2 : 4) prepare_ve
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged variant (the product path when T % 4 == 0 and the tile fits shared memory).
+// prepare_vec_kernel is latency-bound: every thread chases its own row loads (ncu: 37 % issue-active, 31 % warps active).
+// Here a CTA owns PREPB_ROWS output rows x all T frames of one mixture; the (at most 2 per output row) input rows it
+// needs -- and only those: on the high-frequency half of the axis most input rows are skipped -- are pulled into shared
+// memory by TMA bulk copies (cp.async.bulk, one 4 T-byte row each, issued by the lanes of one warp, completion on one
+// mbarrier), for the mixture and all N sources at once.  With ~48 KB in flight per CTA and several CTAs per SM the HBM
+// pipe stays full without any thread waiting on its own loads; the bilinear taps then read shared memory.
+constexpr int PREPB_ROWS = 8;
+constexpr int PREPB_THREADS = 256;
+constexpr int PREPB_MAX_SMEM = 96 * 1024;
+
+__device__ __forceinline__ void bulk_load_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NS>
+__global__ void __launch_bounds__(PREPB_THREADS) prepare_bulk_kernel(const PrepareParams p) {
+  extern __shared__ __align__(128) float rows_sm[];            // [(NS + 1)][2 * PREPB_ROWS][T]
+  __shared__ __align__(8) unsigned long long bar_storage;
+  __shared__ int row_of_slot[2 * PREPB_ROWS];                  // input row held by each staged slot
+  __shared__ int slot_a[PREPB_ROWS], slot_b[PREPB_ROWS];       // slots of taps y0 / y0 + 1 of each output row (-1: outside the image)
+  const int b = blockIdx.y;
+  const int h0 = blockIdx.x * PREPB_ROWS;
+  const int T = p.T;
+  const uint32_t bar = smem_u32(&bar_storage);
+  const uint32_t row_bytes = (uint32_t)T * 4u;
+  if (threadIdx.x < 32) {
+    // Warp 0 sets the tile up and issues the copies.  Lane e < 16 owns tap (e & 1) of output row (e >> 1); equal input rows
+    // share one staged slot: the lowest lane holding a row is its leader, slots are numbered by leader order.
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    const int r = (lane & 15) >> 1, tap = lane & 1;
+    const int h = min(h0 + r, p.Hout - 1);
+    const int y = __ldg(p.ytap.i0 + h) + tap;
+    const bool valid = lane < 2 * PREPB_ROWS && y >= 0 && y < p.Hin;
+    const unsigned same = __match_any_sync(0xffffffffu, valid ? y : -1000 - lane);
+    const int leader = __ffs(same) - 1;
+    const unsigned leaders = __ballot_sync(0xffffffffu, valid && leader == lane);
+    const int slot = valid ? __popc(leaders & ((1u << leader) - 1u)) : -1;
+    if (lane < 2 * PREPB_ROWS) {
+      if (tap == 0) slot_a[r] = slot; else slot_b[r] = slot;
+      if (valid && leader == lane) row_of_slot[slot] = y;
+    }
+    const int ns = __popc(leaders);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(ns * (NS + 1)) * row_bytes);
+    __syncwarp();
+    for (int i = lane; i < ns * (NS + 1); i += 32) {
+      const int j = i / ns, k = i % ns;
+      const float* base = (j == 0 ? p.mix : p.src[j - 1]) + ((size_t)b * p.Hin + row_of_slot[k]) * T;
+      bulk_load_row(smem_u32(rows_sm + ((size_t)j * 2 * PREPB_ROWS + k) * T), base, row_bytes, bar);
+    }
+  }
+  __syncthreads();                                                       // slot tables and the barrier are visible to every warp
+  // thread = 4 consecutive columns x 2 output rows; the x taps do not depend on the row
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const size_t out_off = (size_t)b * p.Hout * T;
+  // (columns beyond T: threads idle; T <= 256 per pass, wider clips loop)
+  mbar_wait(bar, 0, nullptr, 61);
+  for (int w0 = 4 * tx; w0 < T; w0 += 4 * 64) {
+    const int4 xi = __ldg(reinterpret_cast<const int4*>(p.xtap.i0 + w0));
+    const float4 xf = __ldg(reinterpret_cast<const float4*>(p.xtap.frac + w0));
+    const int sel[4] = {xi.x - (w0 - 1), xi.y - w0, xi.z - (w0 + 1), xi.w - (w0 + 2)};
+    const float fx[4] = {xf.x, xf.y, xf.z, xf.w};
+    auto sample = [&](int j, int slot, float eps, float (&out)[4]) {     // x-interpolated staged row at the 4 columns
+      if (slot < 0) { out[0] = out[1] = out[2] = out[3] = 0.f; return; }
+      const float* r = rows_sm + ((size_t)j * 2 * PREPB_ROWS + slot) * T + w0;
+      const float4 c = *reinterpret_cast<const float4*>(r);
+      float e[6];
+      e[0] = w0 > 0 ? r[-1] + eps : 0.f;                                 // zero padding outside the image: no epsilon there
+      e[1] = c.x + eps; e[2] = c.y + eps; e[3] = c.z + eps; e[4] = c.w + eps;
+      e[5] = w0 + 4 < T ? r[4] + eps : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = sel[q] ? e[q + 1] : e[q];
+        const float c2 = sel[q] ? e[q + 2] : e[q + 1];
+        out[q] = (1.f - fx[q]) * a + fx[q] * c2;
+      }
+    };
+#pragma unroll
+    for (int rr = 0; rr < PREPB_ROWS / 4; ++rr) {
+      const int r = ty + 4 * rr;
+      const int h = h0 + r;
+      if (h >= p.Hout) continue;
+      const float fy = __ldg(p.ytap.frac + h);
+      const int sa = slot_a[r], sb = slot_b[r];
+      float a[4], c[4], mx[4];
+      sample(0, sa, 1e-10f, a);                                          // mag_mix + 1e-10 before the warp (main.py:54)
+      sample(0, sb, 1e-10f, c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx[q] = (1.f - fy) * a[q] + fy * c[q];
+      const size_t o = out_off + (size_t)h * T + w0;
+      if (p.mix_w) *reinterpret_cast<float4*>(p.mix_w + o) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+      if (p.log_mix) *reinterpret_cast<float4*>(p.log_mix + o) = make_float4(fast_log(mx[0]), fast_log(mx[1]), fast_log(mx[2]), fast_log(mx[3]));
+      if (p.weights) {
+        float wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wv[q] = p.weighted ? fminf(fmaxf(fast_log1p_pos(mx[q]), 1e-3f), 10.f) : 1.f;
+        *reinterpret_cast<float4*>(p.weights + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      }
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
+        float sv[4];
+        sample(n + 1, sa, 0.f, a);
+        sample(n + 1, sb, 0.f, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sv[q] = (1.f - fy) * a[q] + fy * c[q];
+        if (p.src_w[n]) *reinterpret_cast<float4*>(p.src_w[n] + o) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+        if (p.gt[n]) {
+          float gv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            gv[q] = p.binary ? (sv[q] > 0.5f * mx[q] ? 1.f : 0.f) : fminf(fmaxf(sv[q] / mx[q], 0.f), 5.f);
+          *reinterpret_cast<float4*>(p.gt[n] + o) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+      }
+    }
+  }
+}
+
+static bool bulk_pointers_ok(const PrepareParams& p, int NS) {
+  // cp.async.bulk needs 16-byte aligned global rows
+  if ((reinterpret_cast<uintptr_t>(p.mix) & 15u) != 0) return false;
+  for (int n = 0; n < NS; ++n)
+    if ((reinterpret_cast<uintptr_t>(p.src[n]) & 15u) != 0) return false;
+  return true;
+}
+
 template <int NS>
 static int launch_prepare(const PrepareParams& p, bool warp, cudaStream_t stream) {
+  const size_t bulk_smem = (size_t)(NS + 1) * 2 * PREPB_ROWS * p.T * sizeof(float);
+  if (warp && (p.T & 3) == 0 && bulk_smem <= (size_t)PREPB_MAX_SMEM && bulk_pointers_ok(p, NS)) {
+    auto kern = prepare_bulk_kernel<NS>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+    dim3 grid(ceil_div(p.Hout, PREPB_ROWS), p.B);
+    kern<<<grid, PREPB_THREADS, bulk_smem, stream>>>(p);
+    AVSEP_LAUNCH_CHECK();
+    return AVSEP_OK;
+  }
   if (warp && (p.T & 3) == 0) {
     dim3 block(PREP_TX, PREP_TY);
     dim3 grid(ceil_div(p.T, PREP_TX * 4), ceil_div(p.Hout, PREP_TY * PREP_ROWS_PER_THREAD), p.B);
