@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import AvsepError, LIB_PATH
 from . import ops
 from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count, list_loss, pcm16_to_wave, pit_loss, pit_lossmat, pit_reorder, pit_search, separate, stft, stft_mix,
-                  synth_masks, synth_masks_loss, synth_nosum, synth_pixelwise)
+                  synth_masks, synth_masks_loss, synth_masks_pit_loss, synth_nosum, synth_pixelwise)
 from . import modules
 from .modules import BCELoss, BaseLoss, Bias, InnerProd, L1Loss, L2Loss, PitWrapper, activate
 from . import hotpath
@@ -29,6 +29,6 @@ __all__ = [
     "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
     "stft", "stft_mix", "istft", "pcm16_to_wave", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
     "_stft", "_mix_n_and_stft", "stft_batch", "get_spec", "prepare_inferdata", "recover_aud", "recover_aud_arrays", "Step", "clip_windows", "assemble_windows", "separate_long_clip",
-    "synth_masks", "synth_masks_loss", "synth_nosum", "synth_pixelwise", "list_loss", "pit_loss", "pit_lossmat",
+    "synth_masks", "synth_masks_loss", "synth_masks_pit_loss", "synth_nosum", "synth_pixelwise", "list_loss", "pit_loss", "pit_lossmat",
     "InnerProd", "Bias", "BaseLoss", "BCELoss", "L1Loss", "L2Loss", "PitWrapper", "activate",
 ]

@@ -85,6 +85,8 @@ SIGNATURES = {
     "avsep_loss_backward": (_I, [_I, _P, _P, _P, _I, _SZ, _P, _P, _P]),
     "avsep_scale_if_needed": (_I, [_P, _SZ, _P, _P]),
     "avsep_pit_lossmat": (_I, [_I, _P, _P, _P, _I, _SZ, _I, _P, _P]),
+    "avsep_synth_forward_pit": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "avsep_plane_gather": (_I, [_P, _P, _P, _F, _I, _I, _SZ, _P, _P]),
     "avsep_pit_search": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "avsep_pit_reorder": (_I, [_P, _P, _I, _SZ, _I, _P, _P]),
     "avsep_pit_backward": (_I, [_I, _P, _P, _P, _P, _P, _I, _SZ, _I, _P, _P]),

@@ -7,6 +7,8 @@
 // [B,K,H,W] outer product per source in the backward; here it is streamed exactly once per pass
 // with 128-bit loads, the K-vector of every source lives in shared memory, the per-channel
 // reductions for d(vec)/d(scale)/d(bias) use warp shuffles, and the loss is reduced in the same pass.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace avsep {
@@ -148,6 +150,100 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const double* __res
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
   const double tot = block_sum<double>(s, red);
   if (threadIdx.x == 0) loss[0] = (float)(tot * inv_count);
+}
+
+// PIT forward (SoP++/main.py:227-236 + PitWrapper._opt_perm_loss, criterion.py:138-176): the N masks of every mixture AND the
+// per-sample N x N loss matrix  lossmat[b][i][j] = mean_HW w * l(pred_j, target_i)  in ONE pass over feat_sound (the reference
+// runs N synthesizer calls, stacks, and materialises [H, W, N, N] repeats per sample).  Same streaming structure as
+// synth_fwd_kernel; the N^2 partial sums leave the CTA as doubles and are reduced in a fixed order by pit_fwd_fin_kernel.
+template <int NS>
+__global__ void __launch_bounds__(SYN_FWD_THREADS)
+synth_fwd_pit_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
+                     const float* __restrict__ bias, int B, int K, int HW, int act, float* __restrict__ out, int loss_kind,
+                     const float* __restrict__ gt, const float* __restrict__ weight, double* __restrict__ partial) {
+  __shared__ float vs[NS][SYN_MAX_K];
+  __shared__ double red[32];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < NS * K; i += blockDim.x) {
+    const int n = i / K, k = i % K;
+    vs[n][k] = vecs[((size_t)b * NS + n) * K + k] * (scale ? scale[k] : 1.f);
+  }
+  __syncthreads();
+  const float bz = bias ? bias[0] : 0.f;
+  const int px = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float lm[NS][NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) lm[i][j] = 0.f;
+  if (px < HW) {
+    float acc[NS][4];
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+    const float* fp = feat + (size_t)b * K * HW + px;
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+      const float4 t4 = ld_stream(reinterpret_cast<const float4*>(fp + (size_t)k * HW));
+      const float f[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
+        const float c = vs[n][k];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[n][e] = fmaf(c, f[e], acc[n][e]);
+      }
+    }
+    float w[4] = {1.f, 1.f, 1.f, 1.f};
+    if (weight) {
+      const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
+      w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+    }
+    float pr[NS][4], tg[NS][4];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      const size_t o = ((size_t)n * B + b) * HW + px;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pr[n][e] = act_apply(act, acc[n][e] + bz);
+      *reinterpret_cast<float4*>(out + o) = make_float4(pr[n][0], pr[n][1], pr[n][2], pr[n][3]);
+      const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
+      tg[n][0] = t4.x; tg[n][1] = t4.y; tg[n][2] = t4.z; tg[n][3] = t4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lm[i][j] += w[e] * loss_elem(loss_kind, pr[j][e], tg[i][e]);
+  }
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const double tot = block_sum<double>((double)lm[i][j], red);
+      if (threadIdx.x == 0) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NS * NS) + i * NS + j] = tot;
+    }
+}
+
+// lossmat[b][q] = (sum over the CTAs of sample b) / HW, fixed order
+__global__ void pit_fwd_fin_kernel(const double* __restrict__ partial, int blocks, int SS, double inv_hw, float* __restrict__ lossmat) {
+  const int b = blockIdx.x, q = threadIdx.x;
+  if (q >= SS) return;
+  double s = 0.0;
+  for (int c = 0; c < blocks; ++c) s += partial[((size_t)b * blocks + c) * SS + q];
+  lossmat[(size_t)b * SS + q] = (float)(s * inv_hw);
+}
+
+// y[j][b][:] = x[sel[b][j]][b][:] (per-sample choice of source plane: targets re-ordered by a PIT permutation, masks by its
+// inverse), optionally times rowscale[b] * factor (per-sample upstream gradients folded into the loss weights)
+__global__ void __launch_bounds__(256) plane_gather_kernel(const float* __restrict__ x, const int* __restrict__ sel, const float* __restrict__ rowscale,
+                                                            float factor, int N, int B, size_t P, float* __restrict__ y) {
+  const int b = blockIdx.y, j = blockIdx.z;
+  const int src = sel ? sel[b * N + j] : j;
+  const float sc = rowscale ? rowscale[b] * factor : 1.f;
+  const float* xp = x + ((size_t)src * B + b) * P;
+  float* yp = y + ((size_t)j * B + b) * P;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) yp[i] = xp[i] * sc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -569,7 +665,7 @@ SynthScratch synth_scratch_layout(int B, int N, int K, int HW) {
   s.bwd_chunks = ceil_div(HW, SYN_BWD_THREADS * 4 * SYN_BWD_ITERS);
   s.Kp = ceil_div(K, SYN_KCHUNK) * SYN_KCHUNK;
   size_t off = 0;
-  s.loss_partial = off; off = up(off + sizeof(double) * (size_t)B * ceil_div(HW, SYN_FWD_THREADS));   // VEC=1 worst case
+  s.loss_partial = off; off = up(off + sizeof(double) * (size_t)B * ceil_div(HW, SYN_FWD_THREADS) * (size_t)(N > 1 ? N * N : 1));   // VEC=1 worst case; N^2 sums per CTA for the PIT forward
   s.s_partial = off;    off = up(off + sizeof(float) * (size_t)B * s.bwd_chunks * N * s.Kp);
   s.dz_partial = off;   off = up(off + sizeof(float) * (size_t)B * s.bwd_chunks * N);
   s.tvec = off;         off = up(off + sizeof(float) * (size_t)B * N * K);
@@ -792,6 +888,44 @@ int avsep_synth_pixelwise(const float* feat_dev, const float* feats_img_dev, con
   dim3 grid(ceil_div(HW, 256), P, B);
   synth_pixelwise_kernel<<<grid, 256, K * sizeof(float), (cudaStream_t)stream>>>(feat_dev, feats_img_dev, scale_dev, bias_dev, K,
                                                                                  P, HW, out_dev);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+int avsep_synth_forward_pit(const float* feat_dev, const float* vecs_dev, const float* scale_dev, const float* bias_dev, int B, int N,
+                            int K, int HW, int activation, float* out_dev, int loss_kind, const float* gt_dev,
+                            const float* weight_dev, float* lossmat_dev, void* scratch_dev, void* stream_) {
+  AVSEP_REQUIRE(feat_dev && vecs_dev && out_dev && gt_dev && lossmat_dev && scratch_dev, "avsep_synth_forward_pit: null tensor");
+  AVSEP_REQUIRE(N >= 1 && N <= AVSEP_MAX_SRC && K >= 1 && K <= SYN_MAX_K && B >= 0 && B <= 65535, "avsep_synth_forward_pit: bad B / N / K");
+  AVSEP_REQUIRE(HW >= 4 && (HW % 4) == 0, "avsep_synth_forward_pit: H * W = %d must be a multiple of 4", HW);
+  AVSEP_REQUIRE(loss_kind >= AVSEP_LOSS_L1 && loss_kind <= AVSEP_LOSS_BCE, "avsep_synth_forward_pit: unknown loss kind %d", loss_kind);
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const SynthScratch lay = synth_scratch_layout(B, N, K, HW);
+  double* partial = reinterpret_cast<double*>(static_cast<char*>(scratch_dev) + lay.loss_partial);
+  dim3 grid(lay.fwd_blocks_x, B);
+  switch (N) {
+    case 1: synth_fwd_pit_kernel<1><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+    case 2: synth_fwd_pit_kernel<2><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+    case 3: synth_fwd_pit_kernel<3><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+    default: synth_fwd_pit_kernel<4><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+  }
+  AVSEP_LAUNCH_CHECK();
+  pit_fwd_fin_kernel<<<B, 32, 0, stream>>>(partial, lay.fwd_blocks_x, N * N, 1.0 / (double)HW, lossmat_dev);
+  AVSEP_LAUNCH_CHECK();
+  return AVSEP_OK;
+}
+
+int avsep_plane_gather(const float* x_dev, const int* sel_dev, const float* rowscale_dev, float factor, int N, int B, size_t P,
+                       float* y_dev, void* stream) {
+  AVSEP_REQUIRE(x_dev && y_dev && N >= 1 && N <= 65535 && B >= 0 && B <= 65535 && P >= 1, "avsep_plane_gather: bad argument");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return AVSEP_OK;
+  dim3 grid((unsigned)std::min<size_t>((P + 255) / 256, 256), B, N);
+  plane_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, sel_dev, rowscale_dev, factor, N, B, P, y_dev);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }

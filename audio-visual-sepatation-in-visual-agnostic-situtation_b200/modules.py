@@ -51,6 +51,13 @@ class InnerProd(nn.Module):
                                       loss=loss, activation=activation)
         return err, [z[n].unsqueeze(1) for n in range(z.shape[0])]
 
+    def forward_pit(self, ctx_feats, feat_sound, gt_masks, weight, loss='bce', activation='sigmoid'):
+        """Fused audio-only step (SoP++/main.py:227-238: synthesizer loop + sigmoid + PitWrapper + reorder_tensor): returns
+        (err [B], perms, ordered masks as a list of N [B,1,H,W]); one pass over feat_sound forward, one backward."""
+        err, perms, ordered, _ = ops.synth_masks_pit_loss(feat_sound, ctx_feats, self.scale, self.bias, gt_masks, weight,
+                                                          loss=loss, activation=activation)
+        return err, perms, [ordered[n].unsqueeze(1) for n in range(ordered.shape[0])]
+
     def forward_nosum(self, feat_img, feat_sound):
         return ops.synth_nosum(feat_img, feat_sound, self.scale, self.bias)
 

@@ -645,6 +645,93 @@ class _PitLoss(torch.autograd.Function):
         return None, dp, None, None, None, None
 
 
+def _plane_gather(x: torch.Tensor, sel: Optional[torch.Tensor], rowscale: Optional[torch.Tensor] = None, factor: float = 1.0) -> torch.Tensor:
+    """y[j][b] = x[sel[b][j]][b] * (rowscale[b] * factor) for x [N, B, ...] (avsep_plane_gather)."""
+    N, B = x.shape[0], x.shape[1]
+    y = torch.empty_like(x)
+    check(lib.avsep_plane_gather(x.data_ptr(), _p(sel), _p(rowscale), float(factor), N, B, x[0, 0].numel(), y.data_ptr(), _stream()),
+          "avsep_plane_gather")
+    return y
+
+
+class _SynthPitLoss(torch.autograd.Function):
+    """SoP++ audio-only step (SoP++/main.py:227-238): N synthesizer masks + sigmoid + per-sample PIT loss.
+
+    forward: ONE pass over feat_sound gives the masks and the [B,N,N] loss matrix (avsep_synth_forward_pit), the
+    permutation search runs on the device (avsep_pit_search).  backward: with the permutation fixed, the loss is the
+    list-form weighted loss against per-sample re-ordered targets, so the synthesizer's own backward kernel is reused
+    (targets gathered by the inverse permutation, per-sample upstream gradients folded into the weights)."""
+
+    @staticmethod
+    def forward(ctx, feat, vecs, scale, bias, gt, weight, activation, loss_kind):
+        f = _cuda_f32(feat, "synth_pit_loss: feat_sound")
+        v = _cuda_f32(vecs, "synth_pit_loss: vecs")
+        s = _cuda_f32(scale, "synth_pit_loss: scale") if scale is not None else None
+        b = _cuda_f32(bias, "synth_pit_loss: bias") if bias is not None else None
+        g = _cuda_f32(gt, "synth_pit_loss: gt_masks")
+        B, K = f.shape[0], f.shape[1]
+        HW = f[0, 0].numel()
+        N = v.shape[1]
+        w = _cuda_f32(weight, "synth_pit_loss: weight") if weight is not None else torch.ones((B, HW), device=f.device)
+        out = torch.empty((N, B) + tuple(f.shape[2:]), device=f.device, dtype=torch.float32)
+        lossmat = torch.empty((B, N, N), device=f.device, dtype=torch.float32)
+        scratch = _scratch(B, N, K, HW, f.device)
+        check(lib.avsep_synth_forward_pit(f.data_ptr(), v.data_ptr(), _p(s), _p(b), B, N, K, HW, activation, out.data_ptr(), loss_kind,
+                                          g.data_ptr(), w.data_ptr(), lossmat.data_ptr(), scratch.data_ptr(), _stream()),
+              "avsep_synth_forward_pit")
+        loss, perms = pit_search(lossmat)
+        ordered = _plane_gather(out, perms.tensor)                   # ordered[i][b] = out[perm[b][i]][b]  (reorder_tensor)
+        empty = torch.empty(0, device=f.device)
+        ctx.save_for_backward(f, v, s if s is not None else empty, out, g, w, perms.inverse)
+        ctx.has_scale, ctx.has_bias = s is not None, b is not None
+        ctx.activation, ctx.loss_kind = activation, loss_kind
+        ctx.perms = perms
+        ctx.mark_non_differentiable(ordered, lossmat)
+        return loss, ordered, lossmat
+
+    @staticmethod
+    def backward(ctx, gloss, _gord, _glm):
+        f, v, s, out, g, w, inv = ctx.saved_tensors
+        s = s if ctx.has_scale else None
+        B, K = f.shape[0], f.shape[1]
+        HW = f[0, 0].numel()
+        N = v.shape[1]
+        need = ctx.needs_input_grad
+        gl = _cuda_f32(gloss.reshape(B), "synth_pit_loss backward: grad")
+        # loss[b] = 1/(N HW) sum_j sum_px w l(pred_j, gt[inv[b][j]])  =>  sum_b gloss[b] loss[b] is the list-form mean loss over
+        # (N, B, HW) with targets re-ordered per sample and weights scaled by gloss[b] * B
+        gt_perm = _plane_gather(g.reshape(N, B, HW), inv)
+        w_scaled = _plane_gather(w.reshape(1, B, HW), None, gl, float(B)).reshape(B, HW)
+        one = torch.ones(1, device=f.device)
+        dfeat = torch.empty_like(f) if need[0] else None
+        dvecs = torch.empty_like(v) if need[1] else None
+        dscale = torch.empty_like(s) if (s is not None and need[2]) else None
+        dbias = torch.empty(1, device=f.device, dtype=torch.float32) if (ctx.has_bias and need[3]) else None
+        scratch = _scratch(B, N, K, HW, f.device)
+        check(lib.avsep_synth_backward(f.data_ptr(), v.data_ptr(), _p(s), B, N, K, HW, ctx.activation, ctx.loss_kind,
+                                       out.data_ptr(), gt_perm.data_ptr(), w_scaled.data_ptr(), one.data_ptr(), None, _p(dfeat), _p(dvecs),
+                                       _p(dscale), _p(dbias), scratch.data_ptr(), _stream()), "avsep_synth_backward")
+        return dfeat, dvecs, dscale, dbias, None, None, None, None
+
+
+def synth_masks_pit_loss(feat_sound, vecs, scale, bias, gt_masks, weight, *, loss: str = "bce", activation: str = "sigmoid"):
+    """SoP++ audio-only step (SoP++/main.py:227-238), fused: returns (err [B] differentiable, perms (device-backed, see Perms),
+    ordered masks [N,B,*spatial] detached = reorder_tensor(pred_masks, perms), lossmat [B,N,N])."""
+    _check_synth_shapes(feat_sound, vecs, scale)
+    if isinstance(gt_masks, (list, tuple)):
+        gt_masks = torch.stack([g.reshape(g.shape[0], *feat_sound.shape[2:]) for g in gt_masks], dim=0)
+    N, B = vecs.shape[1], feat_sound.shape[0]
+    if gt_masks.numel() != N * B * feat_sound[0, 0].numel():
+        raise _lib.AvsepError(f"synth_masks_pit_loss: gt_masks has {gt_masks.numel()} elements, expected [N,B,*spatial]")
+    if feat_sound[0, 0].numel() % 4 != 0:
+        raise _lib.AvsepError("synth_masks_pit_loss: H * W must be a multiple of 4")
+    if loss not in ("bce", "l1", "l2"):
+        raise Exception("Architecture undefined!")     # models/__init__.py:129
+    err, ordered, lossmat = _SynthPitLoss.apply(feat_sound, vecs, scale, bias, gt_masks, weight, ACTIVATIONS[activation], LOSS_KINDS[loss])
+    perms = err.grad_fn.perms if err.grad_fn is not None and hasattr(err.grad_fn, "perms") else pit_search(lossmat)[1]
+    return err, perms, ordered, lossmat
+
+
 def pit_loss(kind: str, preds: torch.Tensor, targets: torch.Tensor, weights: torch.Tensor):
     """PitWrapper.forward (criterion.py:202-231): returns (loss [B], differentiable in preds; perms list of tuples).
 

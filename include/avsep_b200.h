@@ -223,6 +223,20 @@ int avsep_scale_if_needed(float* x_dev, size_t n, const float* gscale_dev, void*
 int avsep_pit_lossmat(int loss_kind, const float* preds_dev, const float* targets_dev,
                       const float* weights_dev, int B, size_t P, int S, float* lossmat_dev, void* stream);
 
+/* SoP++ audio-only step, forward (SoP++/main.py:227-236 + PitWrapper._opt_perm_loss, models/criterion.py:138-176): all N
+ * synthesizer masks of every mixture AND the per-sample N x N PIT loss matrix
+ *   lossmat[b][i][j] = mean_HW weight * l(act(z_j), gt_i)
+ * in ONE pass over feat_sound.  Layouts as avsep_synth_forward (out / gt [N,B,HW], weight [B,HW] or NULL, H*W % 4 == 0);
+ * lossmat_dev [B,N,N] feeds avsep_pit_search.  scratch_dev: avsep_synth_scratch_bytes(B, N, K, HW). */
+int avsep_synth_forward_pit(const float* feat_dev, const float* vecs_dev, const float* scale_dev, const float* bias_dev,
+                            int B, int N, int K, int HW, int activation, float* out_dev, int loss_kind,
+                            const float* gt_dev, const float* weight_dev, float* lossmat_dev, void* scratch_dev,
+                            void* stream);
+/* y[j][b][:] = x[sel[b][j]][b][:] * (rowscale ? rowscale[b] * factor : 1) for x, y [N,B,P]; sel_dev [B,N] int32 or NULL
+ * (identity).  Re-orders source planes per sample by a PIT permutation (PitWrapper.reorder_tensor in the [N,B,...] layout)
+ * and folds per-sample upstream gradients into the loss weights for the backward of the audio-only step. */
+int avsep_plane_gather(const float* x_dev, const int* sel_dev, const float* rowscale_dev, float factor, int N, int B,
+                       size_t P, float* y_dev, void* stream);
 /* PitWrapper._fast_pit (models/criterion.py:113-136) on the device: for every sample the S! permutations in
  * itertools.permutations order, cost = mean_i lossmat[b][i][perm[i]] in fp32, first strict minimum wins.
  *   lossmat_dev [B,S,S] -> loss_dev [B], perm_dev [B,S] (int32), inv_perm_dev [B,S] (int32; what avsep_pit_backward takes).

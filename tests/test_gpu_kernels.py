@@ -404,6 +404,51 @@ def test_pit_matches_reference_golden(golden):
         assert np.array_equal(pw.reorder_tensor(_cuda(pr), [tuple(p_) for p_ in g[f"S{S}_perms"]]).cpu().numpy(), re)
 
 
+@pytest.mark.parametrize("N", [2, 3])
+def test_fused_audio_only_step_equals_synth_then_pitwrapper(N):
+    """SoP++ audio-only step (SoP++/main.py:227-238).  The fused route (masks + S x S loss matrix in one pass over
+    feat_sound, search / reorder / backward on the device) against the reference's sequence built from the already
+    pinned pieces: per-source InnerProd + sigmoid, stack to [B,H,W,S], PitWrapper, mean, reorder_tensor, autograd."""
+    B, K, H, W = 4, 32, 16, 24
+    g = np.random.default_rng(60 + N)
+    feat = g.standard_normal((B, K, H, W)).astype(np.float32)
+    ctx = (1 / (1 + np.exp(-g.standard_normal((B, N, K))))).astype(np.float32)
+    gts = [(g.random((B, 1, H, W)) > 0.5).astype(np.float32) for _ in range(N)]
+    # make the targets of sample 1 best matched by a non-identity permutation of the predictions
+    wgt = np.clip(np.abs(g.standard_normal((B, 1, H, W))), 1e-3, 10).astype(np.float32)
+    net = av.InnerProd(K).cuda()
+    with torch.no_grad():
+        net.scale.copy_(_cuda((1 + 0.1 * g.standard_normal(K)).astype(np.float32)))
+        net.bias.fill_(0.1)
+    up = torch.tensor(g.random(B).astype(np.float32) + 0.5, device="cuda")       # non-uniform per-sample upstream gradient
+    # reference sequence
+    f0, c0 = _cuda(feat).requires_grad_(True), _cuda(ctx).requires_grad_(True)
+    preds = [av.activate(net(c0[:, n], f0), 'sigmoid') for n in range(N)]
+    with torch.no_grad():                                                          # targets = a per-sample permutation of thresholded predictions
+        hard = [(p_ > 0.5).float() for p_ in preds]
+        rot = [hard[(n + 1) % N] for n in range(N)]
+        gts_t = [torch.where((torch.arange(B, device="cuda") % 2 == 1)[:, None, None, None], rot[n], _cuda(gts[n])) for n in range(N)]
+    stacked = torch.stack(preds, dim=-1).squeeze(1)                               # [B,H,W,S]
+    gt_st = torch.stack(gts_t, dim=-1)[:, 0, :]
+    w_st = torch.stack([_cuda(wgt)[:, 0, :]] * N, dim=-1)
+    pw = av.PitWrapper("bce")
+    err0, perms0 = pw(stacked, gt_st, w_st)
+    (err0 * up).sum().backward()
+    ord0 = pw.reorder_tensor(stacked.detach(), perms0)
+    ref_grads = [f0.grad.clone(), c0.grad.clone(), net.scale.grad.clone(), net.bias.grad.clone()]
+    net.zero_grad()
+    # fused route
+    f1, c1 = _cuda(feat).requires_grad_(True), _cuda(ctx).requires_grad_(True)
+    err1, perms1, ordered = net.forward_pit(c1, f1, gts_t, _cuda(wgt))
+    (err1 * up).sum().backward()
+    assert list(perms1) == list(perms0) and any(p_ != tuple(range(N)) for p_ in perms1)
+    assert relerr(err1.detach().cpu().numpy(), err0.detach().cpu().numpy()) < 1e-5
+    for n in range(N):
+        assert relerr(ordered[n][:, 0].cpu().numpy(), ord0[..., n].cpu().numpy()) < 1e-6
+    for a, b_ in zip([f1.grad, c1.grad, net.scale.grad, net.bias.grad], ref_grads):
+        assert relerr(a.cpu().numpy(), b_.cpu().numpy()) < 2e-5
+
+
 def test_pit_search_on_device_matches_itertools_order():
     """avsep_pit_search against the reference's _fast_pit loop (criterion.py:113-136): itertools.permutations order, fp32
     mean, first strict minimum -- including exact ties, which the first permutation must win."""
