@@ -67,12 +67,14 @@ constexpr int FOLD2_TILE_N = 256;      // frames per pair tile of dft_fold3
 // CTAs, each after fence.proxy.async so the generic-proxy stores are visible to the tensor core's async proxy.
 //   warp 0: TMA (basis) | warp 1: MMA issuer | warps 2..9: epilogue | warps 10..10+NPW-1: operand producers
 // ======================================================================================================
+constexpr int FOLD_XT_FLOATS = 32 * 17;   // per-warp transpose tile of the epilogue: 32 bins x (16 frames + 1 pad)
+
 struct Fold3Cfg {
   static constexpr int BK = 32;
   static constexpr int ROW_BYTES = BK * 2;
   static constexpr int SUB_BYTES = FOLD_TILE_M * ROW_BYTES;          // 8 KB: 128 rows x 32 bf16
   static constexpr int STAGE_BYTES = 8 * SUB_BYTES;
-  static constexpr int XPOSE_BYTES = 8 * 32 * 33 * 4;
+  static constexpr int XPOSE_BYTES = 8 * FOLD_XT_FLOATS * 4;          // one [32][17] transpose tile per epilogue warp
   static constexpr int STAGES = (FOLD_SMEM_LIMIT - 1024 - 256 - XPOSE_BYTES) / STAGE_BYTES;
   static constexpr int KSTEPS = FOLD_K / BK;                         // 16
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + XPOSE_BYTES;
@@ -92,6 +94,32 @@ __device__ __forceinline__ float fold3_ldg(const float* p) {
 __device__ __forceinline__ int fold3_reflect(int j, int L) {
   j = abs(j);
   return max(min(j, 2 * (L - 1) - j), 0);
+}
+
+// |re + i im| with MUFU.SQRT (sqrt.approx: max relative error 2^-23, i.e. within 1 ulp): the correctly rounded sqrtf costs ~18
+// instructions, and the epilogue -- which cannot overlap the MMAs because the accumulators fill all 512 TMEM columns -- was
+// instruction-bound on it (clock stamps: 24.5 K cycles of epilogue after 25.5 K cycles of MMAs per tile)
+__device__ __forceinline__ float fold_mag(float re, float im) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(re, re, im * im)));
+  return r;
+}
+
+// A lane owns one bin (TMEM lane) and holds 16 consecutive frames of it; written as they are, the 32 lanes of a store instruction
+// would touch 32 different cache lines (the L1 tag stage pays per line: measured 12 K cycles per tile).  Each warp therefore
+// transposes its 32 bins x 16 frames block through a private padded shared-memory tile, so that one store instruction writes two
+// 64-byte row segments.  xt: this warp's [32][17] floats.
+__device__ __forceinline__ void fold_store_block(float* __restrict__ xt, int lane, const float (&v)[16], float* __restrict__ plane_row0,
+                                                 int T, int t0) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) xt[lane * 17 + j] = v[j];
+  __syncwarp();
+  const int col = lane & 15, sub = lane >> 4;
+  if (t0 + col < T) {
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) __stcs(plane_row0 + (size_t)(r + sub) * T + t0 + col, xt[(r + sub) * 17 + col]);
+  }
+  __syncwarp();
 }
 
 // Waveform loads of one K step of one producer warp.  Lane (sub, c) owns samples n0 = 32 ks + 2 c and n0 + 1 of the
@@ -364,46 +392,33 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
       mbar_wait(tfull_bar, tile_phase, p.err_flag, 45);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;
-      float* xt = xpose_all + (warp - 4) * (32 * 33);
+      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;             // first bin of this warp's 32 TMEM lanes
       const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
-      auto store_block = [&](float* __restrict__ dst, const float (&val)[32], int t0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xt[lane * 33 + j] = val[j];
-        __syncwarp();
-        const int t = t0 + lane;
-        if (t < p.T) {
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) __stcs(dst + ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0 + r) * (size_t)p.T + t, xt[r * 33 + lane]);
-        }
-        __syncwarp();
-      };
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+      const size_t row_off = ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0) * (size_t)p.T;
+      float* xt = xpose_all + (warp - 4) * FOLD_XT_FLOATS;
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
         const int t0 = nt * FOLD2_TILE_N + c0;
         if (t0 >= p.T) break;
-        uint32_t vr[32], vi[32];
-        tmem_ld_32x32b_x32(taddr + c0, vr);
-        tmem_ld_32x32b_x32(taddr + FOLD2_TILE_N + c0, vi);
+        uint32_t vr[16], vi[16];
+        tmem_ld_32x32b_x16(taddr + c0, vr);
+        tmem_ld_32x32b_x16(taddr + FOLD2_TILE_N + c0, vi);
         tmem_ld_wait();
-        float val[32];
+        float val[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float rr = __uint_as_float(vr[j]), ii = __uint_as_float(vi[j]);
-          val[j] = sqrtf(fmaf(rr, rr, ii * ii));
-        }
-        store_block(p.mag, val, t0);
+        for (int j = 0; j < 16; ++j) val[j] = fold_mag(__uint_as_float(vr[j]), __uint_as_float(vi[j]));
+        fold_store_block(xt, lane, val, p.mag + row_off, p.T, t0);
         if (p.phase) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = atan2f(__uint_as_float(vi[j]), __uint_as_float(vr[j]));
-          store_block(p.phase, val, t0);
+          for (int j = 0; j < 16; ++j) val[j] = atan2f(__uint_as_float(vi[j]), __uint_as_float(vr[j]));
+          fold_store_block(xt, lane, val, p.phase + row_off, p.T, t0);
         }
         if (want_reim) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vr[j]);
-          store_block(p.re, val, t0);
+          for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(vr[j]);
+          fold_store_block(xt, lane, val, p.re + row_off, p.T, t0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(vi[j]);
-          store_block(p.im, val, t0);
+          for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(vi[j]);
+          fold_store_block(xt, lane, val, p.im + row_off, p.T, t0);
         }
       }
       tcgen05_fence_before();
@@ -664,54 +679,37 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
       mbar_wait(tfull_bar, tile_phase, p.err_flag, 45);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;
-      float* xt = xpose_all + (warp - 4) * (32 * 33);
-      // which = 0: mixture = |X0 + X1| (the STFT is linear and the mixture IS the sum of its sources), 1 / 2: |X0| / |X1|
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+      const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;             // first bin of this warp's 32 TMEM lanes
+      float* xt = xpose_all + (warp - 4) * FOLD_XT_FLOATS;
+      // planes of p.mag: [mixture | source 0 | source 1] x nmix; mixture = |X0 + X1| (the STFT is linear and the mixture IS the
+      // sum of its sources).  Every accumulator value is read from TMEM once per 16-frame step and feeds all three magnitudes.
+      float* row_mix = p.mag + ((size_t)(0 * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T;
+      float* row_s0 = p.mag + ((size_t)(1 * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T;
+      float* row_s1 = p.mag + ((size_t)(2 * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T;
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
         const int t0 = nt * FOLD3M_TILE_N + c0;
         if (t0 >= p.T) break;
+        // frame c0 + j of the pair tile belongs to CTA `half` (64 frames each): source 0 sits in columns half * 128 + (frame % 64),
+        // source 1 64 columns further; Im is 256 columns after Re
+        const uint32_t col = taddr + (uint32_t)(half * 2 * (FOLD3M_TILE_N / 2) + (c0 - half * (FOLD3M_TILE_N / 2)));
+        uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
+        tmem_ld_32x32b_x16(col, r0v);
+        tmem_ld_32x32b_x16(col + 2 * FOLD3M_TILE_N, i0v);
+        tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2, r1v);
+        tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2 + 2 * FOLD3M_TILE_N, i1v);
+        tmem_ld_wait();
+        float vm[16], v0[16], v1[16];
 #pragma unroll
-        for (int which = 0; which < 3; ++which) {
-#pragma unroll
-          for (int h16 = 0; h16 < 2; ++h16) {
-            // frame c0 + 16 h16 + j of the pair tile belongs to CTA `half` (64 frames each): source 0 sits in columns
-            // half * 128 + (frame % 64), source 1 64 columns further; Im is 256 columns after Re
-            const uint32_t col = taddr + (uint32_t)(half * 2 * (FOLD3M_TILE_N / 2) + (c0 - half * (FOLD3M_TILE_N / 2)) + 16 * h16);
-            uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
-            if (which != 2) {
-              tmem_ld_32x32b_x16(col, r0v);
-              tmem_ld_32x32b_x16(col + 2 * FOLD3M_TILE_N, i0v);
-            }
-            if (which != 1) {
-              tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2, r1v);
-              tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2 + 2 * FOLD3M_TILE_N, i1v);
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float rr, ii;
-              if (which == 0) {
-                rr = __uint_as_float(r0v[j]) + __uint_as_float(r1v[j]);
-                ii = __uint_as_float(i0v[j]) + __uint_as_float(i1v[j]);
-              } else if (which == 1) {
-                rr = __uint_as_float(r0v[j]);
-                ii = __uint_as_float(i0v[j]);
-              } else {
-                rr = __uint_as_float(r1v[j]);
-                ii = __uint_as_float(i1v[j]);
-              }
-              xt[lane * 33 + 16 * h16 + j] = sqrtf(fmaf(rr, rr, ii * ii));
-            }
-          }
-          __syncwarp();
-          const int t = t0 + lane;
-          if (t < p.T) {
-            float* dst = p.mag + ((size_t)(which * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T + t;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) __stcs(dst + (size_t)r * p.T, xt[r * 33 + lane]);
-          }
-          __syncwarp();
+        for (int j = 0; j < 16; ++j) {
+          const float a0 = __uint_as_float(r0v[j]), b0 = __uint_as_float(i0v[j]);
+          const float a1 = __uint_as_float(r1v[j]), b1 = __uint_as_float(i1v[j]);
+          vm[j] = fold_mag(a0 + a1, b0 + b1);
+          v0[j] = fold_mag(a0, b0);
+          v1[j] = fold_mag(a1, b1);
         }
+        fold_store_block(xt, lane, vm, row_mix, p.T, t0);
+        fold_store_block(xt, lane, v0, row_s0, p.T, t0);
+        fold_store_block(xt, lane, v1, row_s1, p.T, t0);
       }
       tcgen05_fence_before();
       mbar_arrive_cluster_relaxed(lead_tempty);
