@@ -62,6 +62,8 @@ SIGNATURES = {
     "avsep_plan_set_fold": (_I, [_P, _I]),
     "avsep_plan_set_inverse_fold": (_I, [_P, _I]),
     "avsep_plan_set_mix_linear": (_I, [_P, _I]),
+    "avsep_plan_set_sm_budget": (_I, [_P, _I]),
+    "avsep_plan_set_spec_staged": (_I, [_P, _I]),
     "avsep_stft_mix": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "avsep_stft": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "avsep_stft_reim": (_I, [_P, _P, _I, _P, _P, _P, _I, _P]),

@@ -346,6 +346,10 @@ __global__ void __launch_bounds__(SPECV_THREADS, 6) spec_prep_vec_kernel(const S
   }
 }
 
+}  // namespace avsep
+#include "spec_prep.cuh"
+namespace avsep {
+
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
@@ -379,7 +383,9 @@ struct avsep_plan {
   bool fold = true;                     // forward transform through the folded kernels
   bool mix_linear = true;               // two-source device-summed mixtures: |X0 + X1| from the two source transforms (dft_fold3m)
   bool inverse_fold = true;             // inverse transform through the folded kernel
+  bool use_spec_tma = true;             // inverse operand through the shared-memory staged kernel (spec_prep.cuh) when it applies
   int generation = 0;                   // bumped by every avsep_plan_set_*: captured CUDA graphs of a step are keyed on it
+  int sm_budget = 0;                    // persistent GEMM grids use at most this many SMs (0 = the whole device): SM-partitioned pipelines
   __nv_bfloat16* basis_fold = nullptr;  // [4 = kind * 2 + split][512 bins][512]
   __nv_bfloat16* basis_ifold = nullptr; // [4 = kind * 2 + split][512 rows in CTA-group order][512 bins]
   __nv_bfloat16* basis_fwd = nullptr;   // plain: [2][1024][1024]  (hi rows 0..1023, lo rows 1024..2047)
@@ -393,10 +399,19 @@ struct avsep_plan {
   int last_mix_B = 0, last_mix_N = 0;
   int* err_flag = nullptr;
   CUtensorMap tm_basis_fold32, tm_basis_ifold, tm_spec_ifold;      // folded kernels
+  CUtensorMap tm_spec_store;                                       // spec_prep_tma_kernel: 64 bins x 32 frames store boxes
+  int unwarp_rmax = -1;                 // most mask rows a 64-bin tile of the un-warp taps (spec_prep_tma_kernel), -1 = not computed
   CUtensorMap tm_basis_fwd, tm_basis_inv, tm_wave2, tm_spec2;      // plain CTA-pair GEMM (128-frame boxes)
   bool tm_wave_valid = false;
   size_t workspace = 0;
 };
+
+// SMs a persistent CTA-pair kernel of this plan may occupy (avsep_plan_set_sm_budget)
+static int plan_pairs(const avsep_plan* pl) {
+  const int sms = avsep::sm_count();
+  return (pl->sm_budget > 0 ? std::min(pl->sm_budget, sms) : sms) / 2;
+}
+
 
 namespace avsep {
 
@@ -456,6 +471,9 @@ static int build_maps(avsep_plan* pl) {
     if (rc) return rc;
     cuuint32_t box3[3] = {(cuuint32_t)IFoldCfg::BK, (cuuint32_t)(IFOLD_TILE_N / 2), 1};
     rc = encode_map(&pl->tm_spec_ifold, pl->spec_split, 3, dims, strides, box3, IFoldCfg::BK);
+    if (rc) return rc;
+    cuuint32_t box_st[3] = {(cuuint32_t)SPT_BINS, (cuuint32_t)SPT_FRAMES, 1};
+    rc = encode_map(&pl->tm_spec_store, pl->spec_split, 3, dims, strides, box_st, 64);
     if (rc) return rc;
   }
   return AVSEP_OK;
@@ -556,7 +574,7 @@ static int launch_ifold(avsep_plan* pl, int S, float* wav_dev, cudaStream_t stre
   ip.out_len = pl->out_len;
   ip.inv_env = pl->inv_env;
   ip.err_flag = pl->err_flag;
-  const int grid2 = 2 * std::min(2 * S, sm_count() / 2);
+  const int grid2 = 2 * std::min(2 * S, plan_pairs(pl));
   if (grid2 <= 0) return AVSEP_OK;
   auto kern = idft_fold2_kernel<IFoldCfg::BK>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IFoldCfg::SMEM_BYTES));
@@ -569,7 +587,7 @@ static int launch_ifold(avsep_plan* pl, int S, float* wav_dev, cudaStream_t stre
 static int launch_fold3(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
   const int n_tiles = ceil_div(prm.T, FOLD2_TILE_N);
   const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
-  const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+  const int grid2 = 2 * std::min(pair_tiles, plan_pairs(pl));
   if (grid2 <= 0) return AVSEP_OK;
   auto kern = dft_fold3_fwd_kernel<2>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
@@ -582,7 +600,7 @@ static int launch_fold3(avsep_plan* pl, const FoldParams& prm, cudaStream_t stre
 static int launch_fold3m(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
   const int n_tiles = ceil_div(prm.T, FOLD3M_TILE_N);
   const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
-  const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+  const int grid2 = 2 * std::min(pair_tiles, plan_pairs(pl));
   if (grid2 <= 0) return AVSEP_OK;
   auto kern = dft_fold3m_fwd_kernel<2>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
@@ -595,7 +613,7 @@ static int launch_fold3m(avsep_plan* pl, const FoldParams& prm, cudaStream_t str
 template <int EPI>
 static int launch_gemm(avsep_plan* pl, const CUtensorMap& tmA, const CUtensorMap& tmB2, DftParams prm, cudaStream_t stream) {
   const int pair_tiles = prm.total_tiles / 2;
-  const int grid2 = 2 * std::min(pair_tiles, sm_count() / 2);
+  const int grid2 = 2 * std::min(pair_tiles, plan_pairs(pl));
   if (grid2 <= 0) return AVSEP_OK;
   auto kern = dft_gemm2_kernel<PLAIN_BK, EPI>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Dft2Cfg<PLAIN_BK, EPI>::SMEM_BYTES));
@@ -752,6 +770,20 @@ int avsep_plan_set_mix_linear(avsep_plan* pl, int enable) {
   return AVSEP_OK;
 }
 
+int avsep_plan_set_sm_budget(avsep_plan* pl, int sms) {
+  AVSEP_REQUIRE(pl != nullptr && sms >= 0 && (sms == 0 || sms >= 2), "avsep_plan_set_sm_budget: bad argument");
+  ++pl->generation;
+  pl->sm_budget = sms;
+  return AVSEP_OK;
+}
+
+int avsep_plan_set_spec_staged(avsep_plan* pl, int enable) {
+  AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_spec_staged: plan is null");
+  ++pl->generation;
+  pl->use_spec_tma = enable != 0;
+  return AVSEP_OK;
+}
+
 int avsep_plan_set_inverse_fold(avsep_plan* pl, int enable) {
   AVSEP_REQUIRE(pl != nullptr, "avsep_plan_set_inverse_fold: plan is null");
   ++pl->generation;
@@ -892,7 +924,28 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
   }
   sp.out = pl->spec_split;
   sp.lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
-  if ((pl->T & 1) == 0) {
+  // staged kernel: (re, im) input, 16-byte aligned rows, and the widest 64-bin tile of the un-warp fits the staging buffer
+  constexpr int kStageFloats = 6144;
+  bool staged = sp.re != nullptr && (pl->T & 3) == 0 && pl->use_spec_tma &&
+                ((reinterpret_cast<uintptr_t>(sp.re) | reinterpret_cast<uintptr_t>(sp.im) | reinterpret_cast<uintptr_t>(sp.masks)) & 15u) == 0;
+  if (staged && sp.log_freq) {
+    if (pl->unwarp_rmax < 0) {
+      std::vector<int> i0(AVSEP_N_BINS);
+      std::vector<float> fr(AVSEP_N_BINS);
+      compute_taps(TAP_UNWARP_Y, 256, AVSEP_N_BINS, i0.data(), fr.data());
+      int rmax = 0;
+      for (int f = 0; f < AVSEP_N_BINS; f += SPT_BINS)
+        rmax = std::max(rmax, std::min(i0[f + SPT_BINS - 1] + 1, 255) - std::max(i0[f], 0) + 1);
+      pl->unwarp_rmax = rmax;
+    }
+    staged = pl->unwarp_rmax * SPT_COLS <= kStageFloats;
+  }
+  if (staged) {
+    const int smem = 1024 + SPT_OUT_BYTES + 2 * SPT_TILE_FLOATS * 4 + kStageFloats * 4;
+    AVSEP_CUDA(cudaFuncSetAttribute(spec_prep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(ceil_div(pl->T, SPT_FRAMES), AVSEP_N_BINS / SPT_BINS, B);
+    spec_prep_tma_kernel<<<grid, SPT_THREADS, smem, stream>>>(pl->tm_spec_store, sp, kStageFloats, pl->max_signals);
+  } else if ((pl->T & 1) == 0) {
     dim3 grid(ceil_div(pl->T, SPECV_FRAMES_PER_CTA), AVSEP_N_BINS / SPECV_BINS_PER_CTA, B);
     spec_prep_vec_kernel<<<grid, SPECV_THREADS, 0, stream>>>(sp);
   } else {

@@ -92,6 +92,14 @@ class Plan:
     def set_mix_linear(self, enable: bool) -> None:
         check(lib.avsep_plan_set_mix_linear(self._h, int(bool(enable))), "avsep_plan_set_mix_linear")
 
+    def set_sm_budget(self, sms: int) -> None:
+        """Persistent transform kernels of this plan use at most `sms` SMs (0 = all): SM-partitioned pipelines."""
+        check(lib.avsep_plan_set_sm_budget(self._h, int(sms)), "avsep_plan_set_sm_budget")
+
+    def set_spec_staged(self, enable: bool) -> None:
+        """Inverse operand through the shared-memory staged kernel (default) or the register-tile kernel (cross-check)."""
+        check(lib.avsep_plan_set_spec_staged(self._h, int(bool(enable))), "avsep_plan_set_spec_staged")
+
     def set_inverse_fold(self, enable: bool) -> None:
         check(lib.avsep_plan_set_inverse_fold(self._h, int(bool(enable))), "avsep_plan_set_inverse_fold")
 

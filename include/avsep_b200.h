@@ -139,6 +139,18 @@ int avsep_plan_set_inverse_fold(avsep_plan* plan, int enable);
  * computed instead of three (dft_fold3m).  0: the mixture waveform is summed and transformed like any other signal.
  * The two routes agree to fp32 rounding (tests/test_gpu_step.py). */
 int avsep_plan_set_mix_linear(avsep_plan* plan, int enable);
+/* SM partitioning: the persistent CTA-pair transforms of this plan (forward and inverse) launch at most sms / 2 pairs
+ * (0 = the whole device, the default).  Used by pipelines that run the data-only front end (the STFT: it depends on the
+ * waveforms, not on the model) of batch i + 1 on one partition of the SMs (a green context, or simply the SMs this
+ * leaves free) while the HBM-bound synthesizer kernels of batch i run on the rest -- the overlap the reference gets
+ * from its DataLoader workers (dataset/base.py:142-147 runs in them while main.py:104-139 trains).  Results do not
+ * depend on the budget (tile order only). */
+int avsep_plan_set_sm_budget(avsep_plan* plan, int sms);
+/* enable = 1 (default): avsep_separate builds the inverse-transform operand (un-warp, threshold, mask x mixture spectrum;
+ * main.py:213-246) with the shared-memory staged kernel (cp.async loads, TMA tensor stores; csrc/spec_prep.cuh) whenever
+ * (re, im) of the mixture are given and T % 4 == 0; 0: always the register-tile kernel (the in-library cross-check: the
+ * two produce identical operands). */
+int avsep_plan_set_spec_staged(avsep_plan* plan, int enable);
 
 /* ---- K2: log-frequency warp + derivations ------------------------------------------------- */
 /* Replaces utils.warpgrid + F.grid_sample (utils.py:12-26; main.py:61-66, 216-220): separable

@@ -48,4 +48,11 @@ for fold in (1, 0):
     key = "folded" if fold else "plain"
     out[key] = dict(separate_ms=t_sep, inverse_gemm_ms=t_inv, spec_prep_ms=t_sep - t_inv,
                     algorithmic_tflops=0.536e9 * S / (t_inv * 1e-3) / 1e12)
+plan.set_inverse_fold(True)
+for staged in (1, 0):                                  # operand kernel: shared-memory staged (TMA stores) vs register tile
+    plan.set_spec_staged(bool(staged))
+    t_sep, t_inv = timeit(sep), timeit(inv)
+    nbytes = B * (N * 256 * T * 4 + 2 * 512 * T * 4 + (N + 1) * T * 1024 * 4)
+    out["spec_staged" if staged else "spec_register_tile"] = dict(spec_prep_ms=t_sep - t_inv, gbytes_per_s=nbytes / (t_sep - t_inv) / 1e6)
+plan.set_spec_staged(True)
 print(json.dumps(out))
