@@ -925,7 +925,7 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
   sp.out = pl->spec_split;
   sp.lo_stride = (size_t)pl->max_signals * pl->T * DFT_K;
   // staged kernel: (re, im) input, 16-byte aligned rows, and the widest 64-bin tile of the un-warp fits the staging buffer
-  constexpr int kStageFloats = 6144;
+  constexpr int kStageFloats = 4608;                     // 18 KB: one source of the widest tile (110 rows x 40), 3 sources elsewhere
   bool staged = sp.re != nullptr && (pl->T & 3) == 0 && pl->use_spec_tma &&
                 ((reinterpret_cast<uintptr_t>(sp.re) | reinterpret_cast<uintptr_t>(sp.im) | reinterpret_cast<uintptr_t>(sp.masks)) & 15u) == 0;
   if (staged && sp.log_freq) {
@@ -941,7 +941,7 @@ int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const f
     staged = pl->unwarp_rmax * SPT_COLS <= kStageFloats;
   }
   if (staged) {
-    const int smem = 1024 + SPT_OUT_BYTES + 2 * SPT_TILE_FLOATS * 4 + kStageFloats * 4;
+    const int smem = 1024 + SPT_OUT_BYTES + 2 * SPT_TILE_FLOATS * 4 + kStageFloats * 4;   // 51 KB: 4 CTAs per SM
     AVSEP_CUDA(cudaFuncSetAttribute(spec_prep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(ceil_div(pl->T, SPT_FRAMES), AVSEP_N_BINS / SPT_BINS, B);
     spec_prep_tma_kernel<<<grid, SPT_THREADS, smem, stream>>>(pl->tm_spec_store, sp, kStageFloats, pl->max_signals);

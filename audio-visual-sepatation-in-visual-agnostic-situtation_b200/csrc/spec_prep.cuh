@@ -22,8 +22,9 @@ namespace avsep {
 constexpr int SPT_BINS = 64, SPT_FRAMES = 32, SPT_THREADS = 128;
 constexpr int SPT_COLS = 40;                                   // staged mask columns: frames [t0 - 4, t0 + 36), 16-byte chunks
 constexpr int SPT_PART_BYTES = SPT_FRAMES * SPT_BINS * 2;      // 4 KB: one (re | im, hi | lo) plane of a signal's tile
-constexpr int SPT_OUT_BYTES = 2 * 4 * SPT_PART_BYTES;          // two signals in flight
+constexpr int SPT_OUT_BYTES = 4 * SPT_PART_BYTES;              // 16 KB: the four planes of one signal's tile
 constexpr int SPT_TILE_FLOATS = SPT_BINS * SPT_FRAMES;         // (re) or (im) tile, [bin][frame]
+static_assert(2 * SPT_TILE_FLOATS * 4 == SPT_OUT_BYTES, "output buffer 1 aliases the (re, im) tile exactly");
 
 __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -58,7 +59,9 @@ __global__ void __launch_bounds__(SPT_THREADS) spec_prep_tma_kernel(const __grid
   __shared__ float s_fy[SPT_BINS];
   const uint32_t base_u32 = (smem_u32(spt_smem_raw) + 1023u) & ~1023u;
   uint8_t* base = spt_smem_raw + (base_u32 - smem_u32(spt_smem_raw));
-  uint8_t* out_sm = base;                                                  // [2 buffers][4 parts][32 frames][128 B], swizzled
+  // output buffers [4 parts][32 frames][128 B], swizzled: buffer 0 is its own, buffer 1 ALIASES the (re, im) tile, which is
+  // dead once every thread holds its cells in registers (load_tile + the barrier of the first finished signal)
+  uint8_t* out_sm = base;
   float* re_sm = reinterpret_cast<float*>(base + SPT_OUT_BYTES);           // [64 bins][32 frames]
   float* im_sm = re_sm + SPT_TILE_FLOATS;
   float* mk_sm = im_sm + SPT_TILE_FLOATS;                                  // staged masks, stage_floats
@@ -101,19 +104,23 @@ __global__ void __launch_bounds__(SPT_THREADS) spec_prep_tma_kernel(const __grid
     }
     cp_async_commit();
   }
+  // division-free: a warp covers 3 rows x 10 chunks (warped masks) or 4 rows x 8 chunks (linear masks) per iteration
   auto stage_masks = [&](int n0, int cnt) {
-    const int chunks_per_row = cols / 4;
-    const int total = cnt * R * chunks_per_row;
-    const int cbase = warped ? t0 - 4 : t0;
-    for (int i = tid; i < total; i += SPT_THREADS) {
-      const int ch = i % chunks_per_row, rr = (i / chunks_per_row) % R, k = i / (chunks_per_row * R);
-      const int col = cbase + 4 * ch;
-      float* dst = mk_sm + (size_t)k * per_src + rr * cols + 4 * ch;
-      const int row = warped ? ylo + rr : f_cta + rr;
-      if (col >= 0 && col < T)
-        cp_async_16(dst, p.masks + (((size_t)(n0 + k) * p.B + b) * p.Hm + row) * (size_t)T + col);
-      else
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);                   // zero padding outside the image
+    const int cpr = cols / 4;                                              // chunks per row: 10 or 8
+    const int rows_per_warp = 32 / cpr;                                    // 3 or 4
+    const int lr = lane / cpr, ch = lane - lr * cpr;
+    const int col = (warped ? t0 - 4 : t0) + 4 * ch;
+    const bool col_ok = col >= 0 && col < T;
+    const int row0 = warped ? ylo : f_cta;
+    if (lr < rows_per_warp) {
+      for (int k = 0; k < cnt; ++k) {
+        const float* src = p.masks + (((size_t)(n0 + k) * p.B + b) * p.Hm + row0) * (size_t)T + col;
+        float* dst = mk_sm + (size_t)k * per_src + 4 * ch;
+        for (int rr = warp * rows_per_warp + lr; rr < R; rr += (SPT_THREADS / 32) * rows_per_warp) {
+          if (col_ok) cp_async_16(dst + rr * cols, src + (size_t)rr * T);
+          else *reinterpret_cast<float4*>(dst + rr * cols) = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding outside the image
+        }
+      }
     }
     cp_async_commit();
   };
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(SPT_THREADS) spec_prep_tma_kernel(const __grid
   };
   // write the thread's 2 frames x 8 bins of one signal into output buffer `buf` (SWIZZLE_128B: chunk ^= frame & 7)
   auto emit = [&](int buf, const float (&mk)[8][2], bool unit) {
-    uint8_t* ob = out_sm + buf * 4 * SPT_PART_BYTES;
+    uint8_t* ob = out_sm + buf * SPT_OUT_BYTES;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       float vre[8], vim[8];
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(SPT_THREADS) spec_prep_tma_kernel(const __grid
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
-      const uint32_t src = base_u32 + (issued & 1) * 4 * SPT_PART_BYTES;
+      const uint32_t src = base_u32 + (issued & 1) * SPT_OUT_BYTES;
       const int sig = b * nsig + jsig;
       tma_store_3d(&tm_out, src + 0 * SPT_PART_BYTES, f_cta, t0, sig);
       tma_store_3d(&tm_out, src + 1 * SPT_PART_BYTES, f_cta, t0, planes + sig);
