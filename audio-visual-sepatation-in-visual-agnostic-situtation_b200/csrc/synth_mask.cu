@@ -44,6 +44,27 @@ __device__ __forceinline__ float loss_grad(int kind, float p, float t) {
   return 2.f * d;
 }
 
+// kernel variants of the loss element / gradient (forward, fused training and PIT kernels): same formulas, MUFU-based logs
+// (3 ulp; the correctly rounded logf / log1pf cost ~50 instructions per mask value and made the forward kernel issue-bound) and, for
+// sigmoid + BCE, the closed form of torch's two-step gradient
+//   (p - t) / max(p (1 - p), 1e-12) * p (1 - p)  ==  (p - t) * min(1, p (1 - p) * 1e12)
+// which keeps the exact zero where the float32 sigmoid saturates.
+__device__ __forceinline__ float loss_elem_fast(int kind, float p, float t) {
+  if (kind == AVSEP_LOSS_BCE) {
+    const float lp = fmaxf(fast_log(p), -100.f);
+    const float l1p = fmaxf(fast_log1m(p), -100.f);
+    return (t - 1.f) * l1p - t * lp;
+  }
+  const float d = p - t;
+  return kind == AVSEP_LOSS_L1 ? fabsf(d) : d * d;
+}
+__device__ __forceinline__ float dz_elem_fast(int kind, int act, float p, float t) {
+  if (kind == AVSEP_LOSS_BCE && act == AVSEP_ACT_SIGMOID) return (p - t) * fminf(1.f, (1.f - p) * p * 1e12f);
+  float d = loss_grad(kind, p, t);
+  if (act == AVSEP_ACT_SIGMOID) d *= (1.f - p) * p;
+  return d;
+}
+
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
   v = warp_sum(v);
@@ -131,7 +152,7 @@ synth_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ vecs,
           t[0] = gt[o];
         }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) ls += w[e] * loss_elem(loss_kind, pr[e], t[e]);
+        for (int e = 0; e < VEC; ++e) ls += w[e] * loss_elem_fast(loss_kind, pr[e], t[e]);
       }
     }
     lsum = (double)ls;
@@ -139,6 +160,110 @@ synth_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ vecs,
   if (loss_kind != AVSEP_LOSS_NONE) {
     const double tot = block_sum<double>(lsum, red);
     if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward (+ loss) with the feat stream staged through shared memory: the eval step and plain InnerProd.forward when
+// K <= 32 and HW % 4 == 0.  synth_fwd_kernel keeps 8 register-staged 128-bit loads in flight per thread and stops at
+// ~0.77-0.82 of the HBM roofline; here, as in synth_train_kernel, every thread sends all K 16-byte feat values of its
+// 4 pixels to a thread-private shared-memory column with cp.async (K loads in flight per thread, no staging registers,
+// no barrier), in two halves so that the second half is still in flight while the first is being accumulated.  Same
+// accumulation order and the same sigmoid as synth_fwd_kernel: identical masks.
+// ---------------------------------------------------------------------------------------------
+constexpr int SYN_FS_THREADS = 128;
+constexpr int SYN_FS_GROUPS = 4;                       // pixel groups of 128 x 4 px walked by one CTA
+constexpr int SYN_FS_SMEM = SYN_KCHUNK * SYN_FS_THREADS * 16;  // 64 KB staging
+
+template <int NS, bool FULLK>
+__global__ void __launch_bounds__(SYN_FS_THREADS, 3)
+synth_fwd_staged_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
+                        const float* __restrict__ bias, int B, int K, int HW, int act, float* __restrict__ out, int loss_kind,
+                        const float* __restrict__ gt, const float* __restrict__ weight, double* __restrict__ partial) {
+  extern __shared__ float4 stage[];                    // [32][SYN_FS_THREADS], column = thread (private)
+  __shared__ float vs[NS][SYN_KCHUNK];
+  __shared__ double red[32];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < NS * SYN_KCHUNK; i += blockDim.x) {
+    const int n = i / SYN_KCHUNK, k = i % SYN_KCHUNK;
+    vs[n][k] = (k < K) ? vecs[((size_t)b * NS + n) * K + k] * (scale ? scale[k] : 1.f) : 0.f;
+  }
+  __syncthreads();
+  const float bz = bias ? bias[0] : 0.f;
+  const float* fbase = feat + (size_t)b * K * HW;
+  constexpr int HALF = SYN_KCHUNK / 2;
+  float lsum = 0.f;
+  auto issue = [&](int px, int k0) {                   // feat[k0 .. k0 + 16) of the thread's 4 pixels -> its column
+#pragma unroll
+    for (int k = k0; k < k0 + HALF; ++k)
+      if (FULLK || k < K) cp_async_16(&stage[k * SYN_FS_THREADS + tid], fbase + (size_t)k * HW + px);
+    cp_async_commit();
+  };
+  auto pixel = [&](int grp) { return ((blockIdx.x * SYN_FS_GROUPS + grp) * SYN_FS_THREADS + tid) * 4; };
+  int px = pixel(0);
+  if (px < HW) { issue(px, 0); issue(px, HALF); }
+#pragma unroll 1
+  for (int grp = 0; grp < SYN_FS_GROUPS; ++grp, px = pixel(grp)) {
+    if (px >= HW) break;                               // pixel groups grow with grp: the later ones are outside too
+    const int px_next = pixel(grp + 1);
+    const bool more = grp + 1 < SYN_FS_GROUPS && px_next < HW;
+    float w[4] = {1.f, 1.f, 1.f, 1.f};
+    float4 tgt[NS];
+    if (loss_kind != AVSEP_LOSS_NONE) {                // small streams overlap the feat loads
+      if (weight) {
+        const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
+        w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+      }
+#pragma unroll
+      for (int n = 0; n < NS; ++n) tgt[n] = *reinterpret_cast<const float4*>(gt + ((size_t)n * B + b) * HW + px);
+    }
+    float z[NS][4];
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) z[n][e] = 0.f;
+    auto accumulate = [&](int k0) {
+#pragma unroll
+      for (int k = k0; k < k0 + HALF; ++k) {
+        if (FULLK || k < K) {
+          const float4 f = stage[k * SYN_FS_THREADS + tid];
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            const float c = vs[n][k];
+            z[n][0] = fmaf(c, f.x, z[n][0]);
+            z[n][1] = fmaf(c, f.y, z[n][1]);
+            z[n][2] = fmaf(c, f.z, z[n][2]);
+            z[n][3] = fmaf(c, f.w, z[n][3]);
+          }
+        }
+      }
+    };
+    asm volatile("cp.async.wait_group 1;" ::: "memory");      // first half landed (the second may still be in flight)
+    accumulate(0);
+    if (more) issue(px_next, 0);                       // the column's first half is free again: next group's loads start now
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
+    accumulate(HALF);
+    if (more) issue(px_next, HALF);
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      const size_t o = ((size_t)n * B + b) * HW + px;
+      float pr[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float zz = z[n][e] + bz;
+        pr[e] = act == AVSEP_ACT_SIGMOID ? __frcp_rn(1.0f + expf(-zz)) : zz;     // == 1 / (1 + exp(-z)), correctly rounded
+      }
+      *reinterpret_cast<float4*>(out + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+      if (loss_kind != AVSEP_LOSS_NONE) {
+        const float tt[4] = {tgt[n].x, tgt[n].y, tgt[n].z, tgt[n].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lsum += w[e] * loss_elem_fast(loss_kind, pr[e], tt[e]);
+      }
+    }
+  }
+  if (loss_kind != AVSEP_LOSS_NONE) {
+    const double tot = block_sum<double>((double)lsum, red);
+    if (tid == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
   }
 }
 
@@ -214,7 +339,7 @@ synth_fwd_pit_kernel(const float* __restrict__ feat, const float* __restrict__ v
 #pragma unroll
       for (int j = 0; j < NS; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) lm[i][j] += w[e] * loss_elem(loss_kind, pr[j][e], tg[i][e]);
+        for (int e = 0; e < 4; ++e) lm[i][j] += w[e] * loss_elem_fast(loss_kind, pr[j][e], tg[i][e]);
   }
 #pragma unroll
   for (int i = 0; i < NS; ++i)
@@ -421,26 +546,6 @@ __global__ void __launch_bounds__(256) synth_bwd_final_kernel(const float* __res
 constexpr int SYN_TR_THREADS = 128;
 constexpr int SYN_TR_GROUPS = 4;                       // pixel groups of 128 x 4 px walked by one CTA
 constexpr int SYN_TR_SMEM = 32 * SYN_TR_THREADS * 16;  // 64 KB staging
-
-// fused-kernel variants of the loss element / gradient: same formulas, MUFU-based logs (3 ulp) and, for
-// sigmoid + BCE, the closed form of torch's two-step gradient
-//   (p - t) / max(p (1 - p), 1e-12) * p (1 - p)  ==  (p - t) * min(1, p (1 - p) * 1e12)
-// which keeps the exact zero where the float32 sigmoid saturates.
-__device__ __forceinline__ float loss_elem_fast(int kind, float p, float t) {
-  if (kind == AVSEP_LOSS_BCE) {
-    const float lp = fmaxf(fast_log(p), -100.f);
-    const float l1p = fmaxf(fast_log1m(p), -100.f);
-    return (t - 1.f) * l1p - t * lp;
-  }
-  const float d = p - t;
-  return kind == AVSEP_LOSS_L1 ? fabsf(d) : d * d;
-}
-__device__ __forceinline__ float dz_elem_fast(int kind, int act, float p, float t) {
-  if (kind == AVSEP_LOSS_BCE && act == AVSEP_ACT_SIGMOID) return (p - t) * fminf(1.f, (1.f - p) * p * 1e12f);
-  float d = loss_grad(kind, p, t);
-  if (act == AVSEP_ACT_SIGMOID) d *= (1.f - p) * p;
-  return d;
-}
 
 template <int NS, bool FULLK>
 __global__ void __launch_bounds__(SYN_TR_THREADS, (NS <= 2 ? 3 : 2))
@@ -680,9 +785,14 @@ static int synth_forward_n(const float* feat, const float* vecs, const float* sc
   const bool vec4 = (HW % 4 == 0);
   const SynthScratch lay = synth_scratch_layout(B, NS, K, HW);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(scratch) + lay.loss_partial);
-  const int bx = vec4 ? lay.fwd_blocks_x : ceil_div(HW, SYN_FWD_THREADS);
+  const bool staged = vec4 && K <= SYN_KCHUNK && (reinterpret_cast<uintptr_t>(feat) & 15u) == 0;
+  const int bx = staged ? ceil_div(HW, SYN_FS_THREADS * 4 * SYN_FS_GROUPS) : (vec4 ? lay.fwd_blocks_x : ceil_div(HW, SYN_FWD_THREADS));
   dim3 grid(bx, B);
-  if (vec4)
+  if (staged) {
+    auto kern = K == SYN_KCHUNK ? synth_fwd_staged_kernel<NS, true> : synth_fwd_staged_kernel<NS, false>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_FS_SMEM));
+    kern<<<grid, SYN_FS_THREADS, SYN_FS_SMEM, stream>>>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt, weight, partial);
+  } else if (vec4)
     synth_fwd_kernel<NS, 4><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt,
                                                                   weight, partial);
   else

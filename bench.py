@@ -42,6 +42,7 @@ T = 256
 HW = 256 * 256
 METRIC = "separated mixtures/sec"
 UNIT = "mixtures/s"
+PIPE_SM_BUDGET = 80        # SMs the STFT of the two-steps-in-flight arm may occupy (tools/pipeline_probe.py: best of 48..80)
 
 # algorithmic bytes / flops per mixture (each boundary tensor touched once, fp32) as a function of N
 SIG_FLOPS = 0.5357e9                              # one [256,1022] x [1022,1024] real-input DFT (or its inverse), fp32-equivalent
@@ -475,6 +476,48 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
         barrier()
         return parallel.max_over_ranks(wall, device=dev), lh
 
+    # ---- device-resident, two steps in flight (overlap the tensor-bound STFT with the HBM-bound synthesizer) ----
+    # The STFT + prepare front end depends on the waveforms only, not on the model, so batch i + 1's STFT may run beside batch
+    # i's synthesizer kernels -- the overlap the reference gets from its DataLoader workers (dataset/base.py:142-147 vs
+    # main.py:104-139).  Two Step objects alternate on two streams, inputs resident in HBM, no host synchronisation inside the
+    # loop; the STFT's persistent grid is capped at PIPE_SM_BUDGET SMs (avsep_plan_set_sm_budget) so the other step's
+    # synthesizer CTAs find free SMs while it runs.  Every step's kernels are the serial step's (bit-identical results);
+    # reported beside `value`, which stays the one-step-at-a-time number.
+    pipelined = None
+    if src_only:
+        for p in pipes:
+            p["step"].set_mix_on_device(True)
+            p["step"].plan.set_sm_budget(PIPE_SM_BUDGET)
+            p["dv"], p["ds"], p["db"], p["ls"] = torch.empty_like(dvecs), torch.empty_like(dscale), torch.empty_like(dbias), torch.zeros(1, device=dev)
+
+        def run_pipe(k):
+            main = torch.cuda.current_stream()
+            for p in pipes:
+                p["stream"].wait_stream(main)
+            for i in range(k):
+                p = pipes[i % 2]
+                with torch.cuda.stream(p["stream"]):
+                    p["step"].train_dev(sources_dev, vecs_dev, feat, scale, bias, p["dfeat"], p["dv"], p["ds"], p["db"], p["ls"])
+            for p in pipes:
+                main.wait_stream(p["stream"])
+
+        run_pipe(max(args.warmup, 4))
+        barrier()
+        y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        y0.record()
+        run_pipe(args.steps)
+        y1.record()
+        barrier()
+        ms_p = parallel.max_over_ranks(y0.elapsed_time(y1), device=dev)
+        pipelined = dict(value=B * world * args.steps / (ms_p * 1e-3), unit=UNIT, ms_per_step=ms_p / args.steps,
+                         loss=[float(pipes[0]["ls"]), float(pipes[1]["ls"])], steps_in_flight=2, stft_sm_budget=PIPE_SM_BUDGET,
+                         note="two steps in flight on two streams, inputs resident in HBM, whole loop timed with CUDA events (fill and "
+                              "drain included); same kernels and bits as `value`; the gain is small because the STFT alone already runs "
+                              "the part into its power cap and the synthesizer kernels lose throughput on fewer SMs "
+                              "(tools/pipeline_probe.py, profiles/r2_pipeline_probe.json)")
+        for p in pipes:
+            p["step"].plan.set_sm_budget(0)
+
     # primary: the host supplies the N source waveforms (fp32), the mixture (their sum, dataset/music.py:127) is formed
     # on the GPU; secondary: the host also supplies the mixture waveform; opt-in: the sources as 16-bit PCM
     ms_e2e, loss_host = timed_e2e("sources")
@@ -589,12 +632,13 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
             kernels.append(kernel_entry(name, N, B, ms, pk, note="not part of the step: the unfused forward / backward pair, for comparison"))
         top = max([k for k in kernels if k["share"] is not None], key=lambda k: k["ms"])
         roofline = roofline_of(top, {"synth_train": "synth_train_kernel", "stft_fwd": "dft_fold3m_fwd_kernel",
-                                     "prepare": "prepare_vec_kernel"}[top["kernel"]], pk,
+                                     "prepare": "prepare_bulk_kernel"}[top["kernel"]], pk,
                                "algorithmic fp32-equivalent FLOPs (0.536 GFLOP/signal)" if top["bound"] == "tensor" else
                                "algorithmic bytes per SURVEY.md section 8(d) (feat_sound counted once: fused fwd+bwd)")
     step.close()
     step_b.close()
     return dict(value=value, ms_total=ms_total, launches=int(launches), loss=loss_val, loss_global=loss_global, explicit=explicit,
+                pipelined=pipelined,
                 e2e=e2e, loss_e2e=dict(sources_only=loss_host, explicit_mixture=loss_host_full, pcm16=loss_host_pcm), clocks=clocks,
                 kernels=kernels, roofline=roofline, src_only=src_only,
                 collective=(dict(per_step="all_reduce([loss, count]) over NCCL, async, inside both timed loops", calls=red.count + red_e.count)
@@ -729,8 +773,8 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
         for name, ms in times.items():
             kernels.append(kernel_entry(name, N, B, ms, pk, share=ms / tot, note=notes.get(name)))
         top = max(kernels, key=lambda k: k["ms"])
-        roofline = roofline_of(top, {"stft_fwd": "dft_fold3_fwd_kernel", "prepare": "prepare_vec_kernel", "synth_fwd_loss": "synth_fwd_kernel",
-                                     "spec_prep": "spec_prep_vec_kernel", "idft_inv": "idft_fold2_kernel"}[top["kernel"]], pk,
+        roofline = roofline_of(top, {"stft_fwd": "dft_fold3_fwd_kernel", "prepare": "prepare_bulk_kernel", "synth_fwd_loss": "synth_fwd_kernel",
+                                     "spec_prep": "spec_prep_tma_kernel", "idft_inv": "idft_fold2_kernel"}[top["kernel"]], pk,
                                "largest kernel of the eval step")
     step.close()
     step_b.close()
@@ -848,7 +892,7 @@ def main_ours(args, rank, world, local):
                                      "formed on the GPU from the 2 device-resident source waveforms (dataset/music.py:127): mixture "
                                      "spectrum = X0 + X1, 2 transforms executed"),
                             l2="inputs larger than L2: 1.3 GB of feat_sound/dfeat streamed per step vs 126 MB L2"),
-                e2e=tr["e2e"], value_explicit_mixture=tr["explicit"], gpu_launches=tr["launches"], clocks=clocks, loss=tr["loss"],
+                e2e=tr["e2e"], value_explicit_mixture=tr["explicit"], value_pipelined=tr["pipelined"], gpu_launches=tr["launches"], clocks=clocks, loss=tr["loss"],
                 loss_global_mean=tr["loss_global"], loss_e2e=tr["loss_e2e"], collective=tr["collective"], roofline=tr["roofline"],
                 kernels=tr["kernels"], eval=ev, cpu_baseline=cpu_baseline, torch_gpu_baseline=gpu_baseline)
         else:
