@@ -42,6 +42,7 @@ T = 256
 HW = 256 * 256
 METRIC = "separated mixtures/sec"
 UNIT = "mixtures/s"
+EVAL_DEPTH = 3             # eval e2e steps in flight: H2D of step i + 2, kernels of i + 1 and D2H of i overlap
 PIPE_SM_BUDGET = 80        # SMs the STFT of the two-steps-in-flight arm may occupy (tools/pipeline_probe.py: best of 48..80)
 
 # algorithmic bytes / flops per mixture (each boundary tensor touched once, fp32) as a function of N
@@ -702,15 +703,16 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     mean_sdr = float(res["sdr"].mean())
     del res
 
-    # ---- e2e: pinned host waveforms + K-vectors in, separated waveforms out to the host, 2 steps in flight ----
-    step_b = av.Step(B, N, K, L)
-    pipes = [dict(step=step, stream=torch.cuda.Stream(), wav=torch.empty((B, N + 1, 65280)).pin_memory()),
-             dict(step=step_b, stream=torch.cuda.Stream(), wav=torch.empty((B, N + 1, 65280)).pin_memory())]
+    # ---- e2e: pinned host waveforms + K-vectors in, separated waveforms out to the host, EVAL_DEPTH steps in flight ----
+    # A step is H2D (134 MB) -> kernels -> D2H (134 MB).  With two steps in flight the H2D engine idles while the older step
+    # drains its D2H; with three the two DMA engines (one per direction) and the SMs are all kept busy.
+    extra = [av.Step(B, N, K, L) for _ in range(EVAL_DEPTH - 1)]
+    pipes = [dict(step=s_, stream=torch.cuda.Stream(), wav=torch.empty((B, N + 1, 65280)).pin_memory()) for s_ in [step] + extra]
 
     def run_e2e(k, to_host):
         for i in range(k):
-            p = pipes[i % 2]
-            p["stream"].synchronize()                              # step i-2 done: its waveforms are on the host now
+            p = pipes[i % EVAL_DEPTH]
+            p["stream"].synchronize()                              # step i - EVAL_DEPTH done: its waveforms are on the host now
             with torch.cuda.stream(p["stream"]):
                 p["step"].eval_host_async(waves_host, vecs_host, feat, scale, bias, p["wav"] if to_host else None)
                 red.push(msum, B)
@@ -720,7 +722,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
 
     def timed_e2e(to_host):
         torch.cuda.synchronize()
-        run_e2e(3, to_host)
+        run_e2e(2 * EVAL_DEPTH, to_host)
         barrier()
         t0 = time.perf_counter()
         run_e2e(args.steps, to_host)
@@ -773,11 +775,12 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
         for name, ms in times.items():
             kernels.append(kernel_entry(name, N, B, ms, pk, share=ms / tot, note=notes.get(name)))
         top = max(kernels, key=lambda k: k["ms"])
-        roofline = roofline_of(top, {"stft_fwd": "dft_fold3_fwd_kernel", "prepare": "prepare_bulk_kernel", "synth_fwd_loss": "synth_fwd_kernel",
+        roofline = roofline_of(top, {"stft_fwd": "dft_fold3_fwd_kernel", "prepare": "prepare_bulk_kernel", "synth_fwd_loss": "synth_fwd_staged_kernel",
                                      "spec_prep": "spec_prep_tma_kernel", "idft_inv": "idft_fold2_kernel"}[top["kernel"]], pk,
                                "largest kernel of the eval step")
     step.close()
-    step_b.close()
+    for s_ in extra:
+        s_.close()
     return dict(
         config=dict(workload="C3 MUSIC+/duet N=3 eval step: STFT(4 signals, mixture re/im kept)+prepare+synth K=32+sigmoid+BCE+un-warp+"
                              "threshold+mask+iSTFT (overlap-add, envelope, trim, clip), then SDR/SIR/SAR/SI-SDR of every clip on the device",
@@ -785,8 +788,8 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
                     l2="inputs larger than L2: 1.07 GB of feat_sound per step vs 126 MB L2"),
         metric=METRIC, unit=UNIT, value=value, ms_per_step=ms_total / args.steps, gpu_launches=int(launches),
         e2e=dict(value=per(ms_e2e), unit=UNIT, ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 pipeline_depth=2, api="avsep_step_eval_host_async (C-ABI): pinned host waveforms [N+1,B,L] + K-vectors in, separated "
-                                       "waveforms [B,N+1,65280] out to pinned host memory; 2 steps in flight on 2 streams",
+                 pipeline_depth=EVAL_DEPTH, api="avsep_step_eval_host_async (C-ABI): pinned host waveforms [N+1,B,L] + K-vectors in, separated "
+                                       f"waveforms [B,N+1,65280] out to pinned host memory; {EVAL_DEPTH} steps in flight on {EVAL_DEPTH} streams",
                  waveforms_stay_on_device=dict(value=per(ms_e2e_dev), ms_per_step=ms_e2e_dev / args.steps, d2h_bytes_per_step=0,
                                                note="same call with wav_host = NULL: what a device-side evaluator consumes")),
         metrics=dict(ms_per_step=ms_met, clips_per_s=B * world / (ms_met * 1e-3), mean_sdr_db=mean_sdr,
