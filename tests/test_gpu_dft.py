@@ -385,6 +385,28 @@ def test_staged_operand_kernel_equals_register_tile_kernel(binary, log_freq, N, 
     assert float(outs[0].abs().max()) > 1e-3
 
 
+def test_sm_budget_does_not_change_results():
+    """avsep_plan_set_sm_budget only caps the persistent grids (tile order): forward and inverse transforms are bit-identical
+    on 48 SMs and on the whole device."""
+    B, N = 3, 2
+    g = torch.Generator(device="cuda").manual_seed(11)
+    src = (torch.rand((N, B, L), device="cuda", generator=g) - 0.5) * 0.8
+    plan = av.ops.Plan((N + 1) * B, L)
+    masks = torch.rand((N, B, 256, 256), device="cuda", generator=g)
+    outs = []
+    for budget in (0, 48):
+        plan.set_sm_budget(budget)
+        mag, _ = av.stft_mix(src, plan=plan)
+        m2, _, re, im = av.stft(src.sum(dim=0), complex_parts=True, plan=plan)
+        wav = av.separate(masks, None, None, re_mix=re, im_mix=im, plan=plan)
+        outs.append((mag.clone(), m2.clone(), wav.clone()))
+    _sync()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    with pytest.raises(av.AvsepError):
+        plan.set_sm_budget(1)
+
+
 def test_separate_with_complex_parts_equals_magphase():
     B, N = 1, 2
     src = O.synth_sources(B, N, seed=8)
