@@ -65,6 +65,7 @@ SIGNATURES = {
     "avsep_plan_set_sm_budget": (_I, [_P, _I]),
     "avsep_plan_set_spec_staged": (_I, [_P, _I]),
     "avsep_stft_mix": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "avsep_stft_mix_reim": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "avsep_stft": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "avsep_stft_reim": (_I, [_P, _P, _I, _P, _P, _P, _I, _P]),
     "avsep_separate": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P]),

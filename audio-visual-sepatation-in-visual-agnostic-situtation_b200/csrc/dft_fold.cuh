@@ -7,7 +7,7 @@
 //
 // Two kernels, both CTA pairs (cta_group::2) that GENERATE the E / O operand themselves from the fp32 waveform:
 //   dft_fold3_fwd_kernel   any batch of signals (eval step, stft / stft_mix with phase or (re, im) outputs)
-//   dft_fold3m_fwd_kernel  two-source mixtures formed on the device: the training step (mixture spectrum = X0 + X1)
+//   dft_fold3m_fwd_kernel  mixtures formed on the device from their 2..4 sources: the training / eval step (mixture spectrum = sum Xn)
 #pragma once
 #include <cuda.h>
 
@@ -437,21 +437,36 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
 
 
 // ======================================================================================================
-// dft_fold3m: dft_fold3 for a MIXTURE THAT IS THE SUM OF ITS TWO SOURCES (dataset/music.py:127 builds every training
-// mixture that way).  The STFT is linear, so the mixture spectrum is X0 + X1 and only the two source transforms are
-// computed: a third less tensor work, waveform traffic and operand conversion than three transforms.
-// Pair tile = 256 bins x 128 frames of BOTH sources of one mixture.  The B tiles of a stage hold the CTA's 64 frames
-// of source 0 in rows 0..63 and of source 1 in rows 64..127 (same 64 KB stage, same producer code as dft_fold3), one
-// N = 256 MMA per product covers both sources, so the Re (TMEM columns [0, 256)) and Im ([256, 512)) accumulators
-// hold [CTA0: source 0 | source 1 | CTA1: source 0 | source 1] x 64 frames, and the epilogue writes three magnitude planes
-// |X0 + X1|, |X0|, |X1| -- the [mixture | source 0 | source 1] layout the rest of the step reads.
+// dft_fold3m: dft_fold3 for a MIXTURE THAT IS THE SUM OF ITS NSRC SOURCES (dataset/music.py:127 builds every training and
+// evaluation mixture that way).  The STFT is linear, so the mixture spectrum is X0 + .. + X(NSRC-1) and only the NSRC source
+// transforms are computed: 1 / (NSRC + 1) less tensor work, waveform traffic and operand conversion.
+// Pair tile = 256 bins x TILE_F frames of ALL sources of one mixture.  The B tiles of a stage hold the CTA's FPC frames of
+// source 0 in rows [0, FPC), of source 1 in [FPC, 2 FPC), ... (same 64 KB stage, same producer code as dft_fold3), one
+// N = 2 NSRC FPC MMA per product covers all sources, so the Re (TMEM columns [0, N)) and Im ([256, 256 + N)) accumulators
+// hold [CTA0: source 0 | source 1 | .. | CTA1: source 0 | ..] x FPC frames, and the epilogue writes the magnitude planes
+// |sum Xn|, |X0|, |X1|, .. -- the [mixture | sources] layout the rest of the step reads -- plus, on request (eval), (re, im)
+// of the mixture spectrum for the inverse transform.
+//   NSRC = 2: FPC = 64 frames per CTA and source, N = 256 (the training step);  NSRC = 3: FPC = 32, N = 192;  NSRC = 4: FPC = 32, N = 256
 // ======================================================================================================
-constexpr int FOLD3M_TILE_N = 128;
+template <int NSRC>
+struct Fold3mShape {
+  static_assert(NSRC >= 2 && NSRC <= 4, "two to four sources per mixture");
+  static constexpr int FPC = NSRC == 2 ? 64 : 32;     // frames per CTA and source
+  static constexpr int ROWS = NSRC * FPC;             // operand rows per CTA: 128 / 96 / 128
+  static constexpr int TILE_F = 2 * FPC;              // frames per pair tile
+  static constexpr int UMMA_N = 2 * ROWS;             // 256 / 192 / 256
+  static constexpr int WPG = ROWS / 32;               // producer warps per group: each converts 32 rows = 32 frames of ONE source
+  static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256 && 2 * WPG <= FOLD3_PW, "tile shape");
+};
+constexpr int FOLD3M_IM_COL = 256;                    // TMEM column of the Im accumulator
 
-template <int NG>
+template <int NG, int NSRC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD3_THREADS, 1)
 dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p) {
+  static_assert(NG == 2, "two producer groups alternate K steps");
   using Cfg = Fold3Cfg;
+  using Sh = Fold3mShape<NSRC>;
+  constexpr int FPC = Sh::FPC, ROWS = Sh::ROWS, TILE_F = Sh::TILE_F, WPG = Sh::WPG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -469,13 +484,13 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const int n_tiles = (p.T + FOLD3M_TILE_N - 1) / FOLD3M_TILE_N;
-  const int nmix = p.num_signals;                  // mixtures; signal planes of p.mag: [mixture | source 0 | source 1] x nmix
+  const int n_tiles = (p.T + TILE_F - 1) / TILE_F;
+  const int nmix = p.num_signals;                  // mixtures; signal planes of p.mag: [mixture | source 0 | source 1 | ..] x nmix
   const int pair_tiles = p.num_signals * n_tiles * (FOLD_M_TILES / 2);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + 2 * (FOLD3_PW / NG));   // TMA expect_tx arrival + the producer warps of the step's group, both CTAs
+      mbar_init(full_bar(s), 1 + 2 * WPG);         // TMA expect_tx arrival + the producer warps of the step's group, both CTAs
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
@@ -497,17 +512,17 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
   setmaxnreg_dec<48>();
   if (warp == 0) {
     // ===================================== TMA producer: basis rows (both CTAs) ================
-    // All 32 lanes first pull the waveform segment of a tile's 128 frames (135 KB, contiguous) into L2, one tile
+    // All 32 lanes first pull the waveform segments of a tile's frames (contiguous per source) into L2, one tile
     // ahead of the producer warps, so their loads never wait on DRAM.
     auto prefetch_tile = [&](int tile) {
       if (!p.prefetch || tile >= pair_tiles) return;
       const int rest = tile / (FOLD_M_TILES / 2);
       const int nt = rest % n_tiles;
       const int b = rest / n_tiles;
-      const int t_first = nt * FOLD3M_TILE_N + (int)rank * (FOLD3M_TILE_N / 2);
+      const int t_first = nt * TILE_F + (int)rank * FPC;
       const int lo = max(t_first * AVSEP_HOP - AVSEP_N_FFT / 2, 0);
-      const int hi = min((t_first + FOLD3M_TILE_N / 2 - 1) * AVSEP_HOP + AVSEP_N_FFT / 2, p.L - 1);
-      for (int src = 0; src < 2; ++src) {
+      const int hi = min((t_first + FPC - 1) * AVSEP_HOP + AVSEP_N_FFT / 2, p.L - 1);
+      for (int src = 0; src < NSRC; ++src) {
         const float* w = p.wave + ((size_t)src * nmix + b) * p.L;
         const char* bb = reinterpret_cast<const char*>(w + lo);
         const char* e = reinterpret_cast<const char*>(w + hi + 1);
@@ -538,7 +553,7 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =======================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, 2 * FOLD3M_TILE_N);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * FOLD_TILE_M, Sh::UMMA_N);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_phase = 0;
@@ -549,12 +564,12 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
           mbar_wait(full_bar(stage), phase, p.err_flag, 43);
           tcgen05_fence_after();
           const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-          // One N = 256 MMA per product covers BOTH sources: the B tile's 128 rows per CTA are [source 0: 64 frames |
-          // source 1: 64 frames], so accumulator columns come out as [CTA0: src0 | src1 | CTA1: src0 | src1] x 64 frames.
-          // (Two N = 128 MMAs, one per source, would read the basis tile from shared memory twice.)
+          // One MMA per product covers ALL sources: the B tile's rows per CTA are [source 0: FPC frames | source 1 | ..], so
+          // accumulator columns come out as [CTA0: src0 | src1 | .. | CTA1: src0 | src1 | ..] x FPC frames.
+          // (One MMA per source would read the basis tile from shared memory NSRC times.)
 #pragma unroll
           for (int kind = 0; kind < 2; ++kind) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(kind * 2 * FOLD3M_TILE_N);               // Re: columns [0, 256), Im: [256, 512)
+            const uint32_t d_tmem = tmem_base + (uint32_t)(kind * FOLD3M_IM_COL);              // Re: columns [0, N), Im: [256, 256 + N)
             const uint64_t a_hi = umma_smem_desc(st + (2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
             const uint64_t a_lo = umma_smem_desc(st + (2 * kind + 1) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
             const uint64_t b_hi = umma_smem_desc(st + (4 + 2 * kind) * Cfg::SUB_BYTES, Cfg::ROW_BYTES);
@@ -578,15 +593,15 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
   }
   } else if (warp >= 12) {
     // ===================================== operand producers: waveform -> E / O hi / lo tiles ==
-    constexpr int WPG = FOLD3_PW / NG;                 // warps per group
-    constexpr int RPW = FOLD3M_TILE_N / WPG;           // rows per producer warp (16 or 32) of the CTA's 2 sources x 64 frames
+    // warp (grp, pw): K steps grp, grp + 2, .., rows [32 pw, 32 pw + 32) = 32 frames of source (32 pw) / FPC
+    constexpr int RPW = 32;
     constexpr int ITER = RPW / 2;                      // a warp covers 2 rows x 32 samples per iteration
     setmaxnreg_inc<104>();
     const int grp = (warp - 12) / WPG;
     const int pw = (warp - 12) % WPG;
     const int sub = lane >> 4, c = lane & 15;
     const int r0 = pw * RPW;
-    const int my_tiles = pair < pair_tiles ? (pair_tiles - pair + npairs - 1) / npairs : 0;
+    const int my_tiles = (pair < pair_tiles && grp < NG) ? (pair_tiles - pair + npairs - 1) / npairs : 0;   // warps beyond 2 WPG: idle
     const int steps = my_tiles * Cfg::KSTEPS;
     float a0[ITER], a1[ITER], b0[ITER], b1[ITER];
     const float* w = p.wave;
@@ -600,8 +615,8 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
         const int rest = tile / (FOLD_M_TILES / 2);
         const int nt = rest % n_tiles;
         const int b = rest / n_tiles;
-        w = p.wave + ((size_t)(r0 / (FOLD3M_TILE_N / 2)) * nmix + b) * p.L;                 // rows 0..63: source 0, 64..127: source 1
-        tbase = nt * FOLD3M_TILE_N + (int)rank * (FOLD3M_TILE_N / 2) + r0 % (FOLD3M_TILE_N / 2) + sub;
+        w = p.wave + ((size_t)(r0 / FPC) * nmix + b) * p.L;                                   // rows [n FPC, (n + 1) FPC): source n
+        tbase = nt * TILE_F + (int)rank * FPC + r0 % FPC + sub;
         // bit i: both frames of iteration i lie in [2, (L - 512) / 256], where no sample index leaves the signal
         lin_mask = 0;
         const int t_even = tbase - sub;
@@ -681,35 +696,72 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;             // first bin of this warp's 32 TMEM lanes
       float* xt = xpose_all + (warp - 4) * FOLD_XT_FLOATS;
-      // planes of p.mag: [mixture | source 0 | source 1] x nmix; mixture = |X0 + X1| (the STFT is linear and the mixture IS the
-      // sum of its sources).  Every accumulator value is read from TMEM once per 16-frame step and feeds all three magnitudes.
-      float* row_mix = p.mag + ((size_t)(0 * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T;
-      float* row_s0 = p.mag + ((size_t)(1 * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T;
-      float* row_s1 = p.mag + ((size_t)(2 * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T;
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
-        const int t0 = nt * FOLD3M_TILE_N + c0;
+      // planes of p.mag: [mixture | source 0 | source 1 | ..] x nmix; mixture = |X0 + X1 + ..| (the STFT is linear and the mixture IS
+      // the sum of its sources).  Every accumulator value is read from TMEM once per 16-frame step and feeds its source's and
+      // the mixture's magnitude (and, for eval, the mixture's (re, im)).
+      auto plane = [&](int j) { return p.mag + ((size_t)(j * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T; };
+      const bool want_reim = p.re != nullptr;
+      const size_t reim_off = ((size_t)b * AVSEP_N_BINS + f0) * (size_t)p.T;
+      // frames [half FPC, half FPC + FPC) of the pair tile belong to CTA `half`: source n sits in columns half ROWS + n FPC + frame,
+      // Im 256 columns after Re
+      for (int c0 = 0; c0 < FPC; c0 += 16) {
+        const int t0 = nt * TILE_F + half * FPC + c0;
         if (t0 >= p.T) break;
-        // frame c0 + j of the pair tile belongs to CTA `half` (64 frames each): source 0 sits in columns half * 128 + (frame % 64),
-        // source 1 64 columns further; Im is 256 columns after Re
-        const uint32_t col = taddr + (uint32_t)(half * 2 * (FOLD3M_TILE_N / 2) + (c0 - half * (FOLD3M_TILE_N / 2)));
-        uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
-        tmem_ld_32x32b_x16(col, r0v);
-        tmem_ld_32x32b_x16(col + 2 * FOLD3M_TILE_N, i0v);
-        tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2, r1v);
-        tmem_ld_32x32b_x16(col + FOLD3M_TILE_N / 2 + 2 * FOLD3M_TILE_N, i1v);
-        tmem_ld_wait();
-        float vm[16], v0[16], v1[16];
+        const uint32_t col = taddr + (uint32_t)(half * ROWS + c0);
+        if constexpr (NSRC == 2) {
+          uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
+          tmem_ld_32x32b_x16(col, r0v);
+          tmem_ld_32x32b_x16(col + FOLD3M_IM_COL, i0v);
+          tmem_ld_32x32b_x16(col + FPC, r1v);
+          tmem_ld_32x32b_x16(col + FPC + FOLD3M_IM_COL, i1v);
+          tmem_ld_wait();
+          float vm[16], v0[16], v1[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a0 = __uint_as_float(r0v[j]), b0 = __uint_as_float(i0v[j]);
-          const float a1 = __uint_as_float(r1v[j]), b1 = __uint_as_float(i1v[j]);
-          vm[j] = fold_mag(a0 + a1, b0 + b1);
-          v0[j] = fold_mag(a0, b0);
-          v1[j] = fold_mag(a1, b1);
+          for (int j = 0; j < 16; ++j) {
+            const float a0 = __uint_as_float(r0v[j]), b0 = __uint_as_float(i0v[j]);
+            const float a1 = __uint_as_float(r1v[j]), b1 = __uint_as_float(i1v[j]);
+            vm[j] = fold_mag(a0 + a1, b0 + b1);
+            v0[j] = fold_mag(a0, b0);
+            v1[j] = fold_mag(a1, b1);
+          }
+          fold_store_block(xt, lane, vm, plane(0), p.T, t0);
+          fold_store_block(xt, lane, v0, plane(1), p.T, t0);
+          fold_store_block(xt, lane, v1, plane(2), p.T, t0);
+          if (want_reim) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vm[j] = __uint_as_float(r0v[j]) + __uint_as_float(r1v[j]);
+            fold_store_block(xt, lane, vm, p.re + reim_off, p.T, t0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vm[j] = __uint_as_float(i0v[j]) + __uint_as_float(i1v[j]);
+            fold_store_block(xt, lane, vm, p.im + reim_off, p.T, t0);
+          }
+        } else {
+          float sr[16], si[16];
+#pragma unroll
+          for (int n = 0; n < NSRC; ++n) {
+            uint32_t rv[16], iv[16];
+            tmem_ld_32x32b_x16(col + n * FPC, rv);
+            tmem_ld_32x32b_x16(col + n * FPC + FOLD3M_IM_COL, iv);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(rv[j]), bi = __uint_as_float(iv[j]);
+              v[j] = fold_mag(a, bi);
+              sr[j] = n == 0 ? a : sr[j] + a;
+              si[j] = n == 0 ? bi : si[j] + bi;
+            }
+            fold_store_block(xt, lane, v, plane(1 + n), p.T, t0);
+          }
+          float vm[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vm[j] = fold_mag(sr[j], si[j]);
+          fold_store_block(xt, lane, vm, plane(0), p.T, t0);
+          if (want_reim) {
+            fold_store_block(xt, lane, sr, p.re + reim_off, p.T, t0);
+            fold_store_block(xt, lane, si, p.im + reim_off, p.T, t0);
+          }
         }
-        fold_store_block(xt, lane, vm, row_mix, p.T, t0);
-        fold_store_block(xt, lane, v0, row_s0, p.T, t0);
-        fold_store_block(xt, lane, v1, row_s1, p.T, t0);
       }
       tcgen05_fence_before();
       mbar_arrive_cluster_relaxed(lead_tempty);

@@ -596,17 +596,27 @@ static int launch_fold3(avsep_plan* pl, const FoldParams& prm, cudaStream_t stre
   return AVSEP_OK;
 }
 
-// forward transform of a device-summed two-source mixture batch (see dft_fold3m in dft_fold.cuh)
-static int launch_fold3m(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
-  const int n_tiles = ceil_div(prm.T, FOLD3M_TILE_N);
+// forward transform of a device-summed mixture batch from its NSRC sources alone (see dft_fold3m in dft_fold.cuh)
+template <int NSRC>
+static int launch_fold3m_n(avsep_plan* pl, const FoldParams& prm, cudaStream_t stream) {
+  const int n_tiles = ceil_div(prm.T, Fold3mShape<NSRC>::TILE_F);
   const int pair_tiles = prm.num_signals * n_tiles * (FOLD_M_TILES / 2);
   const int grid2 = 2 * std::min(pair_tiles, plan_pairs(pl));
   if (grid2 <= 0) return AVSEP_OK;
-  auto kern = dft_fold3m_fwd_kernel<2>;
+  auto kern = dft_fold3m_fwd_kernel<2, NSRC>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Fold3Cfg::SMEM_BYTES));
   kern<<<grid2, FOLD3_THREADS, Fold3Cfg::SMEM_BYTES, stream>>>(pl->tm_basis_fold32, prm);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
+}
+
+static int launch_fold3m(avsep_plan* pl, const FoldParams& prm, int nsrc, cudaStream_t stream) {
+  switch (nsrc) {
+    case 2: return launch_fold3m_n<2>(pl, prm, stream);
+    case 3: return launch_fold3m_n<3>(pl, prm, stream);
+    case 4: return launch_fold3m_n<4>(pl, prm, stream);
+    default: return set_error(AVSEP_ERR_INVALID, "launch_fold3m: %d sources per mixture (2..4 supported)", nsrc);
+  }
 }
 
 // the plain 1024 x 1024 CTA-pair GEMM (cross-check of the folded kernels, raw-accumulator debug hook)
@@ -819,11 +829,16 @@ int stft_impl(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev, floa
   pl->last_wave = wave_dev;
   pl->last_mix_B = mix_B;
   pl->last_mix_N = mix_N;
-  if (pl->fold && pl->mix_linear && mix_N == 2 && S == 3 * mix_B && !phase_dev && !re_dev) {
-    // magnitudes of [mixture | source 0 | source 1] from TWO transforms: the mixture is the sum of its sources
+  if (pl->fold && pl->mix_linear && mix_N >= 2 && mix_N <= 4 && S == (mix_N + 1) * mix_B && !phase_dev &&
+      (!re_dev || reim_count == mix_B)) {
+    // magnitudes of [mixture | source 0 | source 1 | ..] (and, for eval, (re, im) of the mixture) from the mix_N SOURCE
+    // transforms alone: the mixture is the sum of its sources and the STFT is linear
     FoldParams fp = fold_params(pl, mix_B, mag_dev);
     fp.wave = wave_dev;
-    return launch_fold3m(pl, fp, stream);
+    fp.re = re_dev;
+    fp.im = im_dev;
+    fp.reim_count = re_dev ? mix_B : 0;
+    return launch_fold3m(pl, fp, mix_N, stream);
   }
   if (pl->fold) {
     FoldParams fp = fold_params(pl, S, mag_dev);
@@ -878,6 +893,13 @@ int avsep_stft_reim(avsep_plan* pl, const float* wave_dev, int S, float* mag_dev
 int avsep_stft_mix(avsep_plan* pl, const float* sources_dev, int B, int N, float* mag_dev, float* phase_dev, void* stream) {
   AVSEP_REQUIRE(B >= 0 && N >= 1 && N <= AVSEP_MAX_SRC, "avsep_stft_mix: bad B = %d / N = %d", B, N);
   return stft_impl(pl, sources_dev, (N + 1) * B, mag_dev, phase_dev, nullptr, nullptr, 0, stream, B, N);
+}
+
+int avsep_stft_mix_reim(avsep_plan* pl, const float* sources_dev, int B, int N, float* mag_dev, float* re_dev, float* im_dev,
+                        void* stream) {
+  AVSEP_REQUIRE(B >= 0 && N >= 1 && N <= AVSEP_MAX_SRC, "avsep_stft_mix_reim: bad B = %d / N = %d", B, N);
+  AVSEP_REQUIRE(re_dev && im_dev, "avsep_stft_mix_reim: re_dev and im_dev are required");
+  return stft_impl(pl, sources_dev, (N + 1) * B, mag_dev, nullptr, re_dev, im_dev, B, stream, B, N);
 }
 
 int avsep_separate(avsep_plan* pl, const float* masks_dev, int N, int B, const float* mag_dev, const float* phase_dev,

@@ -632,7 +632,7 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
         for name, ms in {"synth_fwd_loss": t_fwd, "synth_bwd": t_bwd}.items():
             kernels.append(kernel_entry(name, N, B, ms, pk, note="not part of the step: the unfused forward / backward pair, for comparison"))
         top = max([k for k in kernels if k["share"] is not None], key=lambda k: k["ms"])
-        roofline = roofline_of(top, {"synth_train": "synth_train_kernel", "stft_fwd": "dft_fold3m_fwd_kernel",
+        roofline = roofline_of(top, {"synth_train": "synth_train_kernel", "stft_fwd": "dft_fold3m_fwd_kernel<2, 2>",
                                      "prepare": "prepare_bulk_kernel"}[top["kernel"]], pk,
                                "algorithmic fp32-equivalent FLOPs (0.536 GFLOP/signal)" if top["bound"] == "tensor" else
                                "algorithmic bytes per SURVEY.md section 8(d) (feat_sound counted once: fused fwd+bwd)")
@@ -660,6 +660,14 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     vecs_dev = vecs_host.to(dev)
     wav_dev = torch.empty((B, N + 1, 65280), device=dev)
     step = av.Step(B, N, K, L)
+    # As in the train arm, the step is handed the N SOURCE waveforms and forms the mixture on the GPU (dataset/music.py:127: the
+    # evaluation mixtures are sums of their sources too): the mixture spectrum -- magnitude and the (re, im) the inverse
+    # transform consumes -- is the sum of the three source transforms (dft_fold3m<3>), three transforms instead of four.
+    # --explicit-mixture hands the mixture waveform over as a fourth signal; that number is reported beside `value` either way.
+    src_only = not args.explicit_mixture
+    step.set_mix_on_device(src_only)
+    sources_dev, sources_host = waves_dev[1:], waves_host[1:]
+    in_dev, in_host = (sources_dev, sources_host) if src_only else (waves_dev, waves_host)
 
     def barrier():
         if world > 1:
@@ -668,8 +676,24 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
 
     red = Reducer(dist, world, dev, 5)
     msum = torch.zeros(4, device=dev)                              # per-step metric sums (filled by the evaluator below)
+    explicit = None
+    if src_only:                                                   # the explicit-mixture reading first, then the default
+        step.set_mix_on_device(False)
+        for _ in range(max(args.warmup, 3)):
+            step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(args.steps):
+            step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        x1.record()
+        barrier()
+        ms_x = parallel.max_over_ranks(x0.elapsed_time(x1), device=dev)
+        explicit = dict(value=B * world * args.steps / (ms_x * 1e-3), unit=UNIT, ms_per_step=ms_x / args.steps,
+                        note="mixture waveform resident in HBM as a fourth signal: four STFTs per mixture")
+        step.set_mix_on_device(True)
     for _ in range(max(args.warmup, 3)):
-        step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        step.eval_dev(in_dev, vecs_dev, feat, scale, bias, wav_dev)
     for _ in range(2):
         red.push(msum, B)
     red.finish()
@@ -678,7 +702,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        step.eval_dev(in_dev, vecs_dev, feat, scale, bias, wav_dev)
         red.push(msum, B)                                          # [sdr, sir, sar, si_sdr sums, clip count] of the step
     e1.record()
     red.finish()
@@ -707,6 +731,8 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     # A step is H2D (134 MB) -> kernels -> D2H (134 MB).  With two steps in flight the H2D engine idles while the older step
     # drains its D2H; with three the two DMA engines (one per direction) and the SMs are all kept busy.
     extra = [av.Step(B, N, K, L) for _ in range(EVAL_DEPTH - 1)]
+    for s_ in extra:
+        s_.set_mix_on_device(src_only)
     pipes = [dict(step=s_, stream=torch.cuda.Stream(), wav=torch.empty((B, N + 1, 65280)).pin_memory()) for s_ in [step] + extra]
 
     def run_e2e(k, to_host):
@@ -714,7 +740,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
             p = pipes[i % EVAL_DEPTH]
             p["stream"].synchronize()                              # step i - EVAL_DEPTH done: its waveforms are on the host now
             with torch.cuda.stream(p["stream"]):
-                p["step"].eval_host_async(waves_host, vecs_host, feat, scale, bias, p["wav"] if to_host else None)
+                p["step"].eval_host_async(in_host, vecs_host, feat, scale, bias, p["wav"] if to_host else None)
                 red.push(msum, B)
         for p in pipes:
             p["stream"].synchronize()
@@ -734,7 +760,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     ms_e2e = timed_e2e(True)
     ms_e2e_dev = timed_e2e(False)
     per = lambda ms: B * world * args.steps / (ms * 1e-3)
-    h2d = waves_host.numel() * 4 + vecs_host.numel() * 4
+    h2d = in_host.numel() * 4 + vecs_host.numel() * 4
     d2h = B * (N + 1) * 65280 * 4
 
     kernels, roofline = [], None
@@ -745,7 +771,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
         mag = torch.empty((S, 512, T), device=dev)
         re = torch.empty((B, 512, T), device=dev)
         im = torch.empty((B, 512, T), device=dev)
-        step.eval_dev(waves_dev, vecs_dev, feat, scale, bias, wav_dev)
+        step.eval_dev(in_dev, vecs_dev, feat, scale, bias, wav_dev)
         pred = step.buffer("pred_masks")
         gt = step.buffer("gt_masks")
         wts = step.buffer("weights")
@@ -757,7 +783,10 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
         mw = av._lib.ptr_array([outs[3 + n].data_ptr() for n in range(N)])
         gg = av._lib.ptr_array([outs[3 + N + n].data_ptr() for n in range(N)])
         masks_out = torch.empty((N, B, HW), device=dev)
-        t_stft = time_calls(lambda: chk(lib.avsep_stft_reim(plan, waves_dev.data_ptr(), S, mag.data_ptr(), re.data_ptr(), im.data_ptr(), B, stream)), 10)
+        if src_only:
+            t_stft = time_calls(lambda: chk(lib.avsep_stft_mix_reim(plan, sources_dev.data_ptr(), B, N, mag.data_ptr(), re.data_ptr(), im.data_ptr(), stream)), 10)
+        else:
+            t_stft = time_calls(lambda: chk(lib.avsep_stft_reim(plan, waves_dev.data_ptr(), S, mag.data_ptr(), re.data_ptr(), im.data_ptr(), B, stream)), 10)
         t_prep = time_calls(lambda: chk(lib.avsep_prepare(mag.data_ptr(), mags, N, B, T, 1, 1, 1, outs[0].data_ptr(), mw,
                                                           outs[1].data_ptr(), outs[2].data_ptr(), gg, stream)), 10)
         t_fwd = time_calls(lambda: chk(lib.avsep_synth_forward(feat.data_ptr(), vecs_dev.data_ptr(), scale.data_ptr(), bias.data_ptr(),
@@ -768,27 +797,35 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
         t_inv = time_calls(lambda: chk(lib.avsep_debug_gemm_only(plan, 1, S, wav_dev.data_ptr(), stream)), 10)
         times = {"stft_fwd": t_stft, "prepare": t_prep, "synth_fwd_loss": t_fwd, "spec_prep": max(t_sep - t_inv, 1e-6), "idft_inv": t_inv}
         tot = sum(times.values())
-        notes = {"stft_fwd": "three-signal-per-source-count folded transform with the operand generated in the kernel; also writes (re, im) of "
-                             "the mixture for the inverse transform",
+        notes = {"stft_fwd": ("folded transform with the operand generated in the kernel, N source transforms for N + 1 spectra (mixture "
+                              "spectrum = sum of the source spectra, dft_fold3m<3>): executes 1.5 x N / (N + 1) = 1.125 x algorithmic; also "
+                              "writes (re, im) of the mixture for the inverse transform") if src_only else
+                             ("folded transform of the N + 1 signals with the operand generated in the kernel (executes 1.5 x algorithmic); "
+                              "also writes (re, im) of the mixture for the inverse transform"),
                  "spec_prep": "timed as avsep_separate minus the inverse GEMM alone (the C-ABI has no entry point for it alone)",
                  "idft_inv": "folded inverse GEMM with the overlap-add in the epilogue (idft_fold2_kernel)"}
         for name, ms in times.items():
-            kernels.append(kernel_entry(name, N, B, ms, pk, share=ms / tot, note=notes.get(name)))
+            kernels.append(kernel_entry(name, N, B, ms, pk, share=ms / tot, note=notes.get(name),
+                                        executed=(1.5 * N / (N + 1) if src_only else 1.5) if name == "stft_fwd" else None))
         top = max(kernels, key=lambda k: k["ms"])
-        roofline = roofline_of(top, {"stft_fwd": "dft_fold3_fwd_kernel", "prepare": "prepare_bulk_kernel", "synth_fwd_loss": "synth_fwd_staged_kernel",
+        roofline = roofline_of(top, {"stft_fwd": "dft_fold3m_fwd_kernel<2, 3>" if src_only else "dft_fold3_fwd_kernel", "prepare": "prepare_bulk_kernel", "synth_fwd_loss": "synth_fwd_staged_kernel",
                                      "spec_prep": "spec_prep_tma_kernel", "idft_inv": "idft_fold2_kernel"}[top["kernel"]], pk,
                                "largest kernel of the eval step")
     step.close()
     for s_ in extra:
         s_.close()
     return dict(
-        config=dict(workload="C3 MUSIC+/duet N=3 eval step: STFT(4 signals, mixture re/im kept)+prepare+synth K=32+sigmoid+BCE+un-warp+"
+        config=dict(workload="C3 MUSIC+/duet N=3 eval step: STFT (" + ("3 source transforms, mixture spectrum = X0 + X1 + X2" if src_only else
+                             "4 signals") + ", mixture re/im kept)+prepare+synth K=32+sigmoid+BCE+un-warp+"
                              "threshold+mask+iSTFT (overlap-add, envelope, trim, clip), then SDR/SIR/SAR/SI-SDR of every clip on the device",
+                    mixture=("formed on the GPU from the 3 device-resident source waveforms (dataset/music.py:127)" if src_only else
+                             "explicit mixture waveform (--explicit-mixture)"),
                     batch_per_gpu=B, global_batch=B * world, num_mix=N, K=K, samples=L, stft="1022/256", grid="256x256",
                     l2="inputs larger than L2: 1.07 GB of feat_sound per step vs 126 MB L2"),
         metric=METRIC, unit=UNIT, value=value, ms_per_step=ms_total / args.steps, gpu_launches=int(launches),
+        value_explicit_mixture=explicit,
         e2e=dict(value=per(ms_e2e), unit=UNIT, ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 pipeline_depth=EVAL_DEPTH, api="avsep_step_eval_host_async (C-ABI): pinned host waveforms [N+1,B,L] + K-vectors in, separated "
+                 pipeline_depth=EVAL_DEPTH, api="avsep_step_eval_host_async (C-ABI): pinned host " + ("SOURCE waveforms [N,B,L]" if src_only else "waveforms [N+1,B,L]") + " + K-vectors in, separated "
                                        f"waveforms [B,N+1,65280] out to pinned host memory; {EVAL_DEPTH} steps in flight on {EVAL_DEPTH} streams",
                  waveforms_stay_on_device=dict(value=per(ms_e2e_dev), ms_per_step=ms_e2e_dev / args.steps, d2h_bytes_per_step=0,
                                                note="same call with wav_host = NULL: what a device-side evaluator consumes")),

@@ -87,9 +87,14 @@ int avsep_stft_reim(avsep_plan* plan, const float* wave_dev, int S, float* mag_d
 /* STFT of B mixtures given only their N sources (the hand-off of dataset/music.py:120-127, where the mixture IS the
  * sum of the sources): sources_dev [N, B, L] -> mag_dev [(N+1) B, 512, T] with the mixtures in planes [0, B) and source
  * n in planes [(1+n) B, (2+n) B); phase_dev (same layout) is optional.  The mixture waveform is never materialised:
- * with N = 2 and no phase output the mixture spectrum is taken as X0 + X1 (avsep_plan_set_mix_linear), otherwise the
+ * with 2 <= N <= 4 and no phase output the mixture spectrum is taken as the sum of the source spectra (avsep_plan_set_mix_linear), otherwise the
  * staging kernel sums the sources on the fly.  Replaces BaseDataset._mix_n_and_stft (dataset/base.py:174-189) per batch. */
 int avsep_stft_mix(avsep_plan* plan, const float* sources_dev, int B, int N, float* mag_dev, float* phase_dev, void* stream);
+/* The evaluation form of avsep_stft_mix (main.py:213-249 needs the mixture's complex spectrum for the inverse transform):
+ * magnitudes [(N+1) * B, 512, T] as above plus (re, im) of the B mixture spectra, re_dev / im_dev [B, 512, T].  With
+ * 2 <= N <= 4 only the N source transforms run: mixture (re, im) = sum of the source spectra (dft_fold3m). */
+int avsep_stft_mix_reim(avsep_plan* plan, const float* sources_dev, int B, int N, float* mag_dev, float* re_dev, float* im_dev,
+                        void* stream);
 
 /* K4. Replaces the reconstruction loop of calc_metrics (main.py:213-249) + utils.istft_reconstruction
  * (utils.py:101-104): un-warp each predicted mask 256->512 bins (grid_sample with warpgrid(warp=False)),
@@ -133,10 +138,10 @@ int avsep_plan_set_fold(avsep_plan* plan, int enable);
  * 1024 x 1024 contraction into two 512 x 512 ones (half the tensor work), overlap-add fused in the epilogue;
  * 0: the plain 1024 x 1024 inverse DFT GEMM (kept as the in-library cross-check of the folded kernel). */
 int avsep_plan_set_inverse_fold(avsep_plan* plan, int enable);
-/* enable = 1 (default): when a step forms the mixture on the device as the sum of its N = 2 sources
- * (avsep_step_set_mix_on_device; dataset/music.py:127 defines every training mixture that way) and only magnitudes
- * are needed (training), the mixture spectrum is taken as X0 + X1 -- the STFT is linear -- so two transforms are
- * computed instead of three (dft_fold3m).  0: the mixture waveform is summed and transformed like any other signal.
+/* enable = 1 (default): when a step forms the mixture on the device as the sum of its N = 2..4 sources
+ * (avsep_step_set_mix_on_device; dataset/music.py:127 defines every mixture that way) and no phase output is asked for,
+ * the mixture spectrum (magnitude, and (re, im) for the eval step) is taken as the sum of the source spectra -- the STFT
+ * is linear -- so N transforms are computed instead of N + 1 (dft_fold3m).  0: the mixture waveform is summed and transformed like any other signal.
  * The two routes agree to fp32 rounding (tests/test_gpu_step.py). */
 int avsep_plan_set_mix_linear(avsep_plan* plan, int enable);
 /* SM partitioning: the persistent CTA-pair transforms of this plan (forward and inverse) launch at most sms / 2 pairs

@@ -1,0 +1,15 @@
+#!/bin/bash
+# one-GPU check after a forward-transform change: DFT + step parity tests, then the bench
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_dft.py tests/test_gpu_step.py -x -q > gpurun_out/t_fold3m.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/t_fold3m.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_fold3m.json 2> gpurun_out/bench_fold3m.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_fold3m.json').read().strip().splitlines()[-1])
+print('value',d['value'],d['ms_per_step'],'pipelined',d['value_pipelined']['value'],'e2e',d['e2e']['value'])
+for k in d['kernels']: print(' ',k['kernel'],round(k['ms'],4),round(k['frac'],3))
+ev=d['eval']; print('eval',ev['value'],ev['ms_per_step'],'explicit',ev['value_explicit_mixture'],'e2e',ev['e2e']['value'],ev['e2e']['ms_per_step'],ev['e2e']['h2d_bytes_per_step'])
+for k in ev['kernels']: print(' ',k['kernel'],round(k['ms'],4),round(k['frac'],3))
+PY
+tail -3 gpurun_out/bench_fold3m.err
