@@ -11,6 +11,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace avsep {
@@ -109,15 +111,22 @@ __device__ __forceinline__ float fold_mag(float re, float im) {
 // would touch 32 different cache lines (the L1 tag stage pays per line: measured 12 K cycles per tile).  Each warp therefore
 // transposes its 32 bins x 16 frames block through a private padded shared-memory tile, so that one store instruction writes two
 // 64-byte row segments.  xt: this warp's [32][17] floats.
+// TC: frames per clip when known at compile time (256 for the 65 535-sample clips of every BASELINE config), 0 = use T.  With
+// a runtime T every store needs its own 64-bit row * T multiply-add -- ncu's source view of round 2 showed 5.3 IMAD + 2 LEA
+// per STG, 43 % of the epilogue's instructions; with TC the 16 row addresses are one base pointer plus immediates.
+template <int TC>
 __device__ __forceinline__ void fold_store_block(float* __restrict__ xt, int lane, const float (&v)[16], float* __restrict__ plane_row0,
                                                  int T, int t0) {
+  const int Ts = TC ? TC : T;
 #pragma unroll
   for (int j = 0; j < 16; ++j) xt[lane * 17 + j] = v[j];
   __syncwarp();
   const int col = lane & 15, sub = lane >> 4;
-  if (t0 + col < T) {
+  if (t0 + col < Ts) {
+    float* q = plane_row0 + (size_t)sub * Ts + t0 + col;
+    const float* x = xt + sub * 17 + col;
 #pragma unroll
-    for (int r = 0; r < 32; r += 2) __stcs(plane_row0 + (size_t)(r + sub) * T + t0 + col, xt[(r + sub) * 17 + col]);
+    for (int r = 0; r < 32; r += 2) __stcs(q + (size_t)r * Ts, x[r * 17]);
   }
   __syncwarp();
 }
@@ -383,6 +392,11 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t lead_tempty = mapa_shared(tempty_bar, 0);
+    // the whole tile loop once per compile-time frame count: TC = 256 (every BASELINE clip) turns the store addresses into
+    // base + immediate; TC = 0 is the general path
+    auto run = [&](auto tc) {
+    constexpr int TC = decltype(tc)::value;
+    const int Tt = TC ? TC : p.T;
     uint32_t tile_phase = 0;
     for (int tile = pair; tile < pair_tiles; tile += npairs) {
       const int mp = tile % (FOLD_M_TILES / 2);
@@ -394,11 +408,11 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int f0 = (2 * mp + (int)rank) * FOLD_TILE_M + 32 * q;             // first bin of this warp's 32 TMEM lanes
       const bool want_reim = p.re != nullptr && (s + p.sig_base) < p.reim_count;
-      const size_t row_off = ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0) * (size_t)p.T;
+      const size_t row_off = ((size_t)(s + p.sig_base) * AVSEP_N_BINS + f0) * (size_t)Tt;
       float* xt = xpose_all + (warp - 4) * FOLD_XT_FLOATS;
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
         const int t0 = nt * FOLD2_TILE_N + c0;
-        if (t0 >= p.T) break;
+        if (t0 >= Tt) break;
         uint32_t vr[16], vi[16];
         tmem_ld_32x32b_x16(taddr + c0, vr);
         tmem_ld_32x32b_x16(taddr + FOLD2_TILE_N + c0, vi);
@@ -406,25 +420,27 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
         float val[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) val[j] = fold_mag(__uint_as_float(vr[j]), __uint_as_float(vi[j]));
-        fold_store_block(xt, lane, val, p.mag + row_off, p.T, t0);
+        fold_store_block<TC>(xt, lane, val, p.mag + row_off, Tt, t0);
         if (p.phase) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) val[j] = atan2f(__uint_as_float(vi[j]), __uint_as_float(vr[j]));
-          fold_store_block(xt, lane, val, p.phase + row_off, p.T, t0);
+          fold_store_block<TC>(xt, lane, val, p.phase + row_off, Tt, t0);
         }
         if (want_reim) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(vr[j]);
-          fold_store_block(xt, lane, val, p.re + row_off, p.T, t0);
+          fold_store_block<TC>(xt, lane, val, p.re + row_off, Tt, t0);
 #pragma unroll
           for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(vi[j]);
-          fold_store_block(xt, lane, val, p.im + row_off, p.T, t0);
+          fold_store_block<TC>(xt, lane, val, p.im + row_off, Tt, t0);
         }
       }
       tcgen05_fence_before();
       mbar_arrive_cluster_relaxed(lead_tempty);
       tile_phase ^= 1u;
     }
+    };
+    if (p.T == 256) run(std::integral_constant<int, 256>{}); else run(std::integral_constant<int, 0>{});
   }
 
   tcgen05_fence_before();
@@ -685,6 +701,10 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t lead_tempty = mapa_shared(tempty_bar, 0);
+    // the whole tile loop once per compile-time frame count (see fold_store_block)
+    auto run = [&](auto tc) {
+    constexpr int TC = decltype(tc)::value;
+    const int Tt = TC ? TC : p.T;
     uint32_t tile_phase = 0;
     for (int tile = pair; tile < pair_tiles; tile += npairs) {
       const int mp = tile % (FOLD_M_TILES / 2);
@@ -699,14 +719,14 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
       // planes of p.mag: [mixture | source 0 | source 1 | ..] x nmix; mixture = |X0 + X1 + ..| (the STFT is linear and the mixture IS
       // the sum of its sources).  Every accumulator value is read from TMEM once per 16-frame step and feeds its source's and
       // the mixture's magnitude (and, for eval, the mixture's (re, im)).
-      auto plane = [&](int j) { return p.mag + ((size_t)(j * nmix + b) * AVSEP_N_BINS + f0) * (size_t)p.T; };
+      auto plane = [&](int j) { return p.mag + ((size_t)(j * nmix + b) * AVSEP_N_BINS + f0) * (size_t)Tt; };
       const bool want_reim = p.re != nullptr;
-      const size_t reim_off = ((size_t)b * AVSEP_N_BINS + f0) * (size_t)p.T;
+      const size_t reim_off = ((size_t)b * AVSEP_N_BINS + f0) * (size_t)Tt;
       // frames [half FPC, half FPC + FPC) of the pair tile belong to CTA `half`: source n sits in columns half ROWS + n FPC + frame,
       // Im 256 columns after Re
       for (int c0 = 0; c0 < FPC; c0 += 16) {
         const int t0 = nt * TILE_F + half * FPC + c0;
-        if (t0 >= p.T) break;
+        if (t0 >= Tt) break;
         const uint32_t col = taddr + (uint32_t)(half * ROWS + c0);
         if constexpr (NSRC == 2) {
           uint32_t r0v[16], i0v[16], r1v[16], i1v[16];
@@ -724,16 +744,16 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
             v0[j] = fold_mag(a0, b0);
             v1[j] = fold_mag(a1, b1);
           }
-          fold_store_block(xt, lane, vm, plane(0), p.T, t0);
-          fold_store_block(xt, lane, v0, plane(1), p.T, t0);
-          fold_store_block(xt, lane, v1, plane(2), p.T, t0);
+          fold_store_block<TC>(xt, lane, vm, plane(0), Tt, t0);
+          fold_store_block<TC>(xt, lane, v0, plane(1), Tt, t0);
+          fold_store_block<TC>(xt, lane, v1, plane(2), Tt, t0);
           if (want_reim) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) vm[j] = __uint_as_float(r0v[j]) + __uint_as_float(r1v[j]);
-            fold_store_block(xt, lane, vm, p.re + reim_off, p.T, t0);
+            fold_store_block<TC>(xt, lane, vm, p.re + reim_off, Tt, t0);
 #pragma unroll
             for (int j = 0; j < 16; ++j) vm[j] = __uint_as_float(i0v[j]) + __uint_as_float(i1v[j]);
-            fold_store_block(xt, lane, vm, p.im + reim_off, p.T, t0);
+            fold_store_block<TC>(xt, lane, vm, p.im + reim_off, Tt, t0);
           }
         } else {
           float sr[16], si[16];
@@ -751,15 +771,15 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
               sr[j] = n == 0 ? a : sr[j] + a;
               si[j] = n == 0 ? bi : si[j] + bi;
             }
-            fold_store_block(xt, lane, v, plane(1 + n), p.T, t0);
+            fold_store_block<TC>(xt, lane, v, plane(1 + n), Tt, t0);
           }
           float vm[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) vm[j] = fold_mag(sr[j], si[j]);
-          fold_store_block(xt, lane, vm, plane(0), p.T, t0);
+          fold_store_block<TC>(xt, lane, vm, plane(0), Tt, t0);
           if (want_reim) {
-            fold_store_block(xt, lane, sr, p.re + reim_off, p.T, t0);
-            fold_store_block(xt, lane, si, p.im + reim_off, p.T, t0);
+            fold_store_block<TC>(xt, lane, sr, p.re + reim_off, Tt, t0);
+            fold_store_block<TC>(xt, lane, si, p.im + reim_off, Tt, t0);
           }
         }
       }
@@ -767,6 +787,8 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
       mbar_arrive_cluster_relaxed(lead_tempty);
       tile_phase ^= 1u;
     }
+    };
+    if (p.T == 256) run(std::integral_constant<int, 256>{}); else run(std::integral_constant<int, 0>{});
   }
 
   tcgen05_fence_before();

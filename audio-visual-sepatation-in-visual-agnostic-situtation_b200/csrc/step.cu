@@ -32,14 +32,24 @@ int synth_backward_impl(const float* feat, const float* vecs, const float* scale
                         cudaStream_t stream);
 }  // namespace avsep
 
+// One captured CUDA graph of a step's kernel sequence, keyed on the argument tuple it was captured with
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  const void* key[16] = {};
+  int launches = 0;            // kernels inside the graph (for the launch counter)
+  void reset() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    memset(key, 0, sizeof(key));
+  }
+};
+
 struct avsep_step {
   int B = 0, N = 0, K = 0, L = 0, T = 0, HW = 0, out_len = 0;
   int mix_on_device = 0;      // waves arguments hold only the N sources; the mixture is summed on the GPU
   int no_fused_train = 0;     // debugging / A-B timing: run the separate forward and backward kernels
-  int use_graph = 0;          // replay the train step as a CUDA graph (non-default streams only)
-  cudaGraphExec_t graph_exec = nullptr;
-  const void* graph_key[13] = {};
-  int graph_launches = 0;
+  int use_graph = 0;          // replay the train / eval step as a CUDA graph (non-default streams only)
+  GraphSlot train_graph, eval_graph;
   avsep_plan* plan = nullptr;
   float* waves = nullptr;     // [N+1, B, L]  (index 0 = mixture)
   float* vecs = nullptr;      // [B, N, K]
@@ -130,11 +140,54 @@ static int pcm16_convert(avsep_step* st, bool with_gains, cudaStream_t stream) {
   return AVSEP_OK;
 }
 
+// A step is a fixed kernel sequence.  With graphs enabled the sequence is captured once per argument tuple (on its second
+// call, after the lazily-created tap tables / operand buffers exist) and replayed with one cudaGraphLaunch, which removes
+// the per-kernel launch gaps (~7 % of a 0.65 ms train step, ~4 % of the 1.2 ms eval step).
+template <typename Body>
+static int run_graphed(avsep_step* st, GraphSlot& g, const void* const (&key)[16], cudaStream_t stream, Body body) {
+  if (!st->use_graph || stream == nullptr || stream == cudaStreamLegacy || stream == cudaStreamPerThread) return body();
+  if (g.exec && memcmp(key, g.key, sizeof(g.key)) == 0) {
+    AVSEP_CUDA(cudaGraphLaunch(g.exec, stream));
+    count_launch(g.launches);
+    return AVSEP_OK;
+  }
+  if (memcmp(key, g.key, sizeof(g.key)) != 0) {            // first call with these arguments: run directly (warm-up)
+    g.reset();
+    memcpy(g.key, key, sizeof(g.key));
+    return body();
+  }
+  // second call with the same arguments: capture, instantiate, launch
+  const uint64_t before = avsep_launch_count();
+  AVSEP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  int rc = body();
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+  if (rc || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    st->use_graph = 0;                                     // capture is not possible here: fall back to plain launches
+    if (rc) return rc;
+    return body();
+  }
+  ce = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    g.exec = nullptr;
+    st->use_graph = 0;
+    cudaGetLastError();
+    return body();
+  }
+  g.launches = (int)(avsep_launch_count() - before);
+  AVSEP_CUDA(cudaGraphLaunch(g.exec, stream));
+  return AVSEP_OK;
+}
+
 extern "C" {
 
 int avsep_step_destroy(avsep_step* st) {
   if (!st) return AVSEP_OK;
-  if (st->graph_exec) cudaGraphExecDestroy(st->graph_exec);
+  st->train_graph.reset();
+  st->eval_graph.reset();
   avsep_plan_destroy(st->plan);
   float* bufs[] = {st->waves, st->vecs, st->mag, st->mix_re, st->mix_im, st->mix_w, st->log_mix, st->weights, st->mags_w,
                    st->gt, st->pred, st->loss, st->one, st->dvecs, st->dscale, st->dbias, st->wav};
@@ -204,63 +257,26 @@ static int train_dev_body(avsep_step* st, const float* waves_dev, const float* v
   return AVSEP_OK;
 }
 
-// The train step is a fixed sequence of 6 kernels + 1 copy.  With graphs enabled the sequence is captured once per
-// argument tuple (on its second call, after the lazily-created tap tables exist) and replayed with one
-// cudaGraphLaunch, which removes the per-kernel launch gaps (~7 % of a 0.65 ms step).
 int avsep_step_train_dev(avsep_step* st, const float* waves_dev, const float* vecs_dev, const float* feat_dev,
                          const float* scale_dev, const float* bias_dev, float* dfeat_dev, float* dvecs_dev, float* dscale_dev,
                          float* dbias_dev, float* loss_dev, void* stream_) {
   AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_train_dev: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!st->use_graph || stream == nullptr || stream == cudaStreamLegacy || stream == cudaStreamPerThread)
-    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
   // the key also carries the plan's variant generation: avsep_plan_set_* after a capture must not replay the old kernels
-  const void* key[13] = {waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev,
+  const void* key[16] = {waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev,
                          (const void*)(uintptr_t)(st->mix_on_device * 2 + st->no_fused_train), (const void*)stream,
                          (const void*)(uintptr_t)plan_generation(st->plan)};
-  if (st->graph_exec && memcmp(key, st->graph_key, sizeof(key)) == 0) {
-    AVSEP_CUDA(cudaGraphLaunch(st->graph_exec, stream));
-    count_launch(st->graph_launches);
-    return AVSEP_OK;
-  }
-  if (memcmp(key, st->graph_key, sizeof(key)) != 0) {      // first call with these arguments: run directly (warm-up)
-    memcpy(st->graph_key, key, sizeof(key));
-    if (st->graph_exec) { cudaGraphExecDestroy(st->graph_exec); st->graph_exec = nullptr; }
+  return run_graphed(st, st->train_graph, key, stream, [&]() {
     return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
-  }
-  // second call with the same arguments: capture, instantiate, launch
-  const uint64_t before = avsep_launch_count();
-  AVSEP_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-  int rc = train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
-  cudaGraph_t graph = nullptr;
-  cudaError_t ce = cudaStreamEndCapture(stream, &graph);
-  if (rc || ce != cudaSuccess || !graph) {
-    if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    st->use_graph = 0;                                     // capture is not possible here: fall back to plain launches
-    if (rc) return rc;
-    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
-  }
-  ce = cudaGraphInstantiate(&st->graph_exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (ce != cudaSuccess) {
-    st->graph_exec = nullptr;
-    st->use_graph = 0;
-    cudaGetLastError();
-    return train_dev_body(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, dfeat_dev, dvecs_dev, dscale_dev, dbias_dev, loss_dev, stream);
-  }
-  st->graph_launches = (int)(avsep_launch_count() - before);
-  AVSEP_CUDA(cudaGraphLaunch(st->graph_exec, stream));
-  return AVSEP_OK;
+  });
 }
 
 int avsep_step_set_graph(avsep_step* st, int enable) {
   AVSEP_REQUIRE(st != nullptr, "avsep_step_set_graph: step is null");
   st->use_graph = enable ? 1 : 0;
-  if (!enable && st->graph_exec) {
-    cudaGraphExecDestroy(st->graph_exec);
-    st->graph_exec = nullptr;
-    memset(st->graph_key, 0, sizeof(st->graph_key));
+  if (!enable) {
+    st->train_graph.reset();
+    st->eval_graph.reset();
   }
   return AVSEP_OK;
 }
@@ -325,10 +341,17 @@ int avsep_step_eval_dev(avsep_step* st, const float* waves_dev, const float* vec
                         void* stream_) {
   AVSEP_REQUIRE(st && waves_dev && vecs_dev && feat_dev, "avsep_step_eval_dev: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, true, stream);
-  if (rc) return rc;
-  return avsep_separate(st->plan, st->pred, st->N, st->B, nullptr, nullptr, st->mix_re, st->mix_im, 1, binary_mask, mask_thres, 1,
-                        wav_dev ? wav_dev : st->wav, stream);
+  uint32_t thres_bits;
+  memcpy(&thres_bits, &mask_thres, sizeof(thres_bits));
+  const void* key[16] = {waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, wav_dev, (const void*)(uintptr_t)thres_bits,
+                         (const void*)(uintptr_t)(st->mix_on_device * 2 + (binary_mask ? 1 : 0)), (const void*)stream,
+                         (const void*)(uintptr_t)plan_generation(st->plan)};
+  return run_graphed(st, st->eval_graph, key, stream, [&]() {
+    int rc = step_forward_common(st, waves_dev, vecs_dev, feat_dev, scale_dev, bias_dev, true, stream);
+    if (rc) return rc;
+    return avsep_separate(st->plan, st->pred, st->N, st->B, nullptr, nullptr, st->mix_re, st->mix_im, 1, binary_mask, mask_thres, 1,
+                          wav_dev ? wav_dev : st->wav, stream);
+  });
 }
 
 int avsep_step_eval_host_async(avsep_step* st, const float* waves_host, const float* vecs_host, const float* feat_dev,

@@ -666,6 +666,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     # --explicit-mixture hands the mixture waveform over as a fourth signal; that number is reported beside `value` either way.
     src_only = not args.explicit_mixture
     step.set_mix_on_device(src_only)
+    step.set_graph(not args.no_graph)                              # eval step replayed as a CUDA graph (side streams only)
     sources_dev, sources_host = waves_dev[1:], waves_host[1:]
     in_dev, in_host = (sources_dev, sources_host) if src_only else (waves_dev, waves_host)
 
@@ -733,6 +734,7 @@ def eval_section(av, parallel, dist, args, rank, world, dev, pk):
     extra = [av.Step(B, N, K, L) for _ in range(EVAL_DEPTH - 1)]
     for s_ in extra:
         s_.set_mix_on_device(src_only)
+        s_.set_graph(not args.no_graph)
     pipes = [dict(step=s_, stream=torch.cuda.Stream(), wav=torch.empty((B, N + 1, 65280)).pin_memory()) for s_ in [step] + extra]
 
     def run_e2e(k, to_host):

@@ -349,7 +349,7 @@ const float* avsep_step_buffer(const avsep_step* step, int which);
  * (dataset/music.py:127: the sum of the sources) is formed on the GPU inside the staging kernel, which saves
  * 1/(N+1) of the H2D bytes.  Default 0: waves = [N+1, B, wave_len] with the mixture at index 0. */
 int avsep_step_set_mix_on_device(avsep_step* step, int enable);
-/* enable = 1: avsep_step_train_dev (and the host variants built on it) capture their kernel sequence into a CUDA
+/* enable = 1: avsep_step_train_dev / avsep_step_eval_dev (and the host variants built on them) capture their kernel sequence into a CUDA
  * graph on the second call with an unchanged argument tuple and replay it afterwards (one cudaGraphLaunch per
  * step).  Only on explicitly created streams (the legacy default stream cannot be captured).  Default 0. */
 int avsep_step_set_graph(avsep_step* step, int enable);

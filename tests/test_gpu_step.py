@@ -208,6 +208,28 @@ def test_eval_host_async_equals_eval_dev():
     st.eval_host_async(torch.from_numpy(waves).pin_memory(), torch.from_numpy(vecs).pin_memory(), c(feat), c(scale), c(bias), None)
     torch.cuda.synchronize()
     assert torch.equal(st.view("wav"), wav_dev)
+    # CUDA-graph replay of the eval step (side stream): same bits as the plain launches, same launch count per step
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        tw, tv, tf, tsc, tb = c(waves), c(vecs), c(feat), c(scale), c(bias)
+        wav_g = torch.empty_like(wav_dev)
+        before = av.launch_count()
+        st.eval_dev(tw, tv, tf, tsc, tb, wav_g)
+        per_step = av.launch_count() - before
+        st.set_graph(True)
+        before = av.launch_count()
+        for _ in range(4):                                         # call 1 direct, call 2 captures + launches, calls 3-4 replay
+            wav_g.zero_()
+            st.eval_dev(tw, tv, tf, tsc, tb, wav_g)
+        side.synchronize()
+        assert av.launch_count() - before == 4 * per_step
+        assert torch.equal(wav_g, wav_dev)
+        st.eval_dev(tw, tv, tf, tsc, tb, wav_g, binary_mask=False)   # a changed argument tuple is not replayed from the old graph
+        side.synchronize()
+        assert not torch.equal(wav_g, wav_dev)
+        st.set_graph(False)
+    torch.cuda.current_stream().wait_stream(side)
     st.close()
 
 
