@@ -284,9 +284,10 @@ dft_fold3_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams p
 #pragma unroll
             for (int k16 = 0; k16 < Cfg::BK / 16; ++k16) {
               const uint64_t adv = (uint64_t)(k16 * 2);
-              umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+              // hi * lo and hi * hi share A = hi: read from shared memory once (operand collector), then lo * hi
+              umma_f16_2sm_keep_a(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+              umma_f16_2sm_reuse_a(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
               umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
           umma_commit_2sm(empty_bar(stage), 3);
@@ -593,9 +594,10 @@ dft_fold3m_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const FoldParams 
 #pragma unroll
             for (int k16 = 0; k16 < Cfg::BK / 16; ++k16) {
               const uint64_t adv = (uint64_t)(k16 * 2);
-              umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+              // hi * lo and hi * hi share A = hi: read from shared memory once (operand collector), then lo * hi
+              umma_f16_2sm_keep_a(d_tmem, a_hi + adv, b_lo + adv, idesc, (ks == 0 && k16 == 0) ? 0u : 1u);
+              umma_f16_2sm_reuse_a(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
               umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
           umma_commit_2sm(empty_bar(stage), 3);
