@@ -322,6 +322,19 @@ class Reducer:
         self.i += 1
         self.count += 1
 
+    def push_packed(self, packed):
+        """Same, for a step that writes its sums straight into packed[:-1] with packed[-1] = the (constant) weight: one D2D
+        copy per step instead of two."""
+        if self.world == 1:
+            return
+        k = self.i % len(self.work)
+        if self.work[k] is not None:
+            self.work[k].wait()
+        self.buf[k].copy_(packed, non_blocking=True)
+        self.work[k] = self.dist.all_reduce(self.buf[k], async_op=True)
+        self.i += 1
+        self.count += 1
+
     def finish(self):
         for w in self.work:
             if w is not None:
@@ -352,7 +365,8 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
     dvecs = torch.empty((B, N, K), device=dev)
     dscale = torch.empty(K, device=dev)
     dbias = torch.empty(1, device=dev)
-    loss = torch.zeros(1, device=dev)
+    loss_count = torch.tensor([0.0, float(B)], device=dev)         # [loss, count]: the step writes its loss into element 0, and the
+    loss = loss_count[:1]                                          # pair is what the per-step all-reduce sends
     dvecs_host = torch.empty((B, N, K)).pin_memory()
     step = av.Step(B, N, K, L)
     step.set_graph(not args.no_graph)                              # train step replayed as a CUDA graph (side streams only)
@@ -391,7 +405,7 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
                 break
     red = Reducer(dist, world, dev, 2)
     for _ in range(3):                                             # warm the collective (NCCL channel setup) outside the timed region
-        red.push(loss, B)
+        red.push_packed(loss_count)
     red.finish()
     barrier()
     launches0 = av.launch_count()
@@ -400,7 +414,7 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
     e0.record()
     for _ in range(args.steps):
         step_dev()
-        red.push(loss, B)                                          # [loss, count] all-reduce of THIS step, inside the timed region
+        red.push_packed(loss_count)                                # [loss, count] all-reduce of THIS step, inside the timed region
     e1.record()
     red_last = red.finish()
     barrier()
@@ -513,7 +527,7 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
         pipelined = dict(value=B * world * args.steps / (ms_p * 1e-3), unit=UNIT, ms_per_step=ms_p / args.steps,
                          loss=[float(pipes[0]["ls"]), float(pipes[1]["ls"])], steps_in_flight=2, stft_sm_budget=PIPE_SM_BUDGET,
                          note="two steps in flight on two streams, inputs resident in HBM, whole loop timed with CUDA events (fill and "
-                              "drain included); same kernels and bits as `value`; the gain is small because the STFT alone already runs "
+                              "drain included; this arm issues no collective); same kernels and bits as `value`; the gain is small because the STFT alone already runs "
                               "the part into its power cap and the synthesizer kernels lose throughput on fewer SMs "
                               "(tools/pipeline_probe.py, profiles/r2_pipeline_probe.json)")
         for p in pipes:

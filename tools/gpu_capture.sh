@@ -13,16 +13,17 @@ CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 timeout 600 $CMD > gpurun_out/plain_bench.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${R}_ncu_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-timeout 600 $CMD > gpurun_out/plain_bench2.log 2>&1 &&
+TCMD="python bench.py --workload train --steps 2 --warmup 1 --no-cpu-baseline"
+timeout 600 $TCMD > gpurun_out/plain_bench2.log 2>&1 &&
 timeout 1500 ncu --set full --clock-control none --import-source on \
-  -k regex:'dft_fold3m_fwd|prepare_bulk_kernel<2>|synth_train_kernel|synth_finalize' \
-  -s 8 -c 4 -f -o gpurun_out/${R}_full_train $CMD > gpurun_out/ncu_full_train.log 2>&1
+  -k regex:'dft_fold3m_fwd|prepare_bulk_kernel|synth_train_kernel|synth_finalize' \
+  -s 8 -c 4 -f -o gpurun_out/${R}_full_train $TCMD > gpurun_out/ncu_full_train.log 2>&1
 echo "full train rc=$?"; tail -2 gpurun_out/ncu_full_train.log | cut -c1-160
 ECMD="python bench.py --workload eval --steps 1 --warmup 1 --no-cpu-baseline"
 timeout 600 $ECMD > gpurun_out/plain_eval.log 2>&1 &&
 timeout 1500 ncu --set full --clock-control none --import-source on \
-  -k regex:'dft_fold3_fwd|prepare_bulk_kernel<3>|synth_fwd_staged|spec_prep_tma|idft_fold2' \
-  -s 5 -c 5 -f -o gpurun_out/${R}_full_eval $ECMD > gpurun_out/ncu_full_eval.log 2>&1
+  -k regex:'dft_fold3m_fwd|dft_fold3_fwd|prepare_bulk_kernel|synth_fwd_staged|spec_prep_tma|idft_fold2' \
+  -s 10 -c 20 -f -o gpurun_out/${R}_full_eval $ECMD > gpurun_out/ncu_full_eval.log 2>&1
 echo "full eval rc=$?"; tail -2 gpurun_out/ncu_full_eval.log | cut -c1-160
 timeout 300 python tools/time_bss.py > gpurun_out/plain_bss.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bss_corr|bss_solve' -s 8 -c 2 -f -o gpurun_out/${R}_full_bss \

@@ -5,8 +5,8 @@ import csv
 import sys
 from collections import defaultdict
 
-STEP = ("dft_fold3m_fwd_kernel", "prepare_bulk_kernel<2>", "synth_train_kernel", "synth_finalize_kernel")
-EVAL = ("dft_fold3_fwd_kernel", "prepare_bulk_kernel<3>", "synth_fwd_staged_kernel<3", "spec_prep_tma_kernel", "idft_fold2_kernel")
+STEP = ("dft_fold3m_fwd_kernel<2, 2>", "prepare_bulk_kernel<2>", "synth_train_kernel", "synth_finalize_kernel")
+EVAL = ("dft_fold3m_fwd_kernel<2, 3>", "prepare_bulk_kernel<3>", "synth_fwd_staged_kernel<3", "spec_prep_tma_kernel", "idft_fold2_kernel")
 
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
 hdr = rows[0]

@@ -17,8 +17,12 @@ def summarise(path):
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     lines = []
+    seen = set()
     for vals in rows[2:]:
         name = vals[hdr.index('Kernel Name')]
+        if name in seen:                      # one block per kernel: the first captured launch
+            continue
+        seen.add(name)
         lines.append(f"kernel: {name}")
         for w in WANT:
             if w in hdr:
