@@ -42,6 +42,7 @@ T = 256
 HW = 256 * 256
 METRIC = "separated mixtures/sec"
 UNIT = "mixtures/s"
+TRAIN_DEPTH = 3            # train e2e steps in flight (each on its own stream)
 EVAL_DEPTH = 3             # eval e2e steps in flight: H2D of step i + 2, kernels of i + 1 and D2H of i overlap
 PIPE_SM_BUDGET = 80        # SMs the STFT of the two-steps-in-flight arm may occupy (tools/pipeline_probe.py: best of 48..80)
 
@@ -445,16 +446,16 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
 
     # ---- end to end through the host-buffer C-ABI entry point (`e2e`) ---------------------------------------
     # Every step copies its pinned host inputs H2D and reads its loss (+ dvecs) back D2H inside the timed
-    # region.  Two Step objects alternate on two streams (a depth-2 software pipeline, like a prefetching
+    # region.  TRAIN_DEPTH Step objects alternate on as many streams (a software pipeline, like a prefetching
     # training loop), so the copy of step i+1 overlaps the kernels of step i; the loss of step i is read on
-    # the host before its Step object is reused for step i+2.  At N > 1 the [loss, count] all-reduce of every step
-    # is issued (asynchronously) inside the loop as well.
-    step_b = av.Step(B, N, K, L)
-    step_b.set_graph(not args.no_graph)
-    pipes = [dict(step=step, stream=torch.cuda.Stream(), dfeat=dfeat, loss=torch.zeros(1).pin_memory(),
-                  dvecs=torch.empty((B, N, K)).pin_memory()),
-             dict(step=step_b, stream=torch.cuda.Stream(), dfeat=torch.empty_like(feat), loss=torch.zeros(1).pin_memory(),
-                  dvecs=torch.empty((B, N, K)).pin_memory())]
+    # the host before its Step object is reused for step i + TRAIN_DEPTH.  (Depth 3 rather than 2: with two steps in flight the
+    # host's wake-up + enqueue after every synchronize sits on the critical path of the faster PCM16 arm.)  At N > 1 the
+    # [loss, count] all-reduce of every step is issued (asynchronously) inside the loop as well.
+    more_steps = [av.Step(B, N, K, L) for _ in range(TRAIN_DEPTH - 1)]
+    for s_ in more_steps:
+        s_.set_graph(not args.no_graph)
+    pipes = [dict(step=s_, stream=torch.cuda.Stream(), dfeat=(dfeat if s_ is step else torch.empty_like(feat)),
+                  loss=torch.zeros(1).pin_memory(), dvecs=torch.empty((B, N, K)).pin_memory()) for s_ in [step] + more_steps]
     for p in pipes:
         p["loss_dev"] = p["step"].view("loss")
     sources_host = waves_host[1:]                                  # [N, B, L] view of the same pinned buffer
@@ -465,8 +466,8 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
         for p in pipes:
             p["step"].set_mix_on_device(mode != "full")
         for i in range(k):
-            p = pipes[i % 2]
-            p["stream"].synchronize()                              # step i-2 done: its loss is on the host now
+            p = pipes[i % TRAIN_DEPTH]
+            p["stream"].synchronize()                              # step i - TRAIN_DEPTH done: its loss is on the host now
             _ = float(p["loss"][0])
             with torch.cuda.stream(p["stream"]):
                 if mode == "pcm16":
@@ -478,11 +479,11 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
         for p in pipes:
             p["stream"].synchronize()
         red_e.finish()
-        return float(pipes[(k - 1) % 2]["loss"][0])
+        return float(pipes[(k - 1) % TRAIN_DEPTH]["loss"][0])
 
     def timed_e2e(mode):
         torch.cuda.synchronize()
-        run_e2e(4, mode)
+        run_e2e(2 * TRAIN_DEPTH, mode)
         barrier()
         t0 = time.perf_counter()
         lh = run_e2e(args.steps, mode)
@@ -500,20 +501,21 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
     # reported beside `value`, which stays the one-step-at-a-time number.
     pipelined = None
     if src_only:
-        for p in pipes:
+        two = pipes[:2]
+        for p in two:
             p["step"].set_mix_on_device(True)
             p["step"].plan.set_sm_budget(PIPE_SM_BUDGET)
             p["dv"], p["ds"], p["db"], p["ls"] = torch.empty_like(dvecs), torch.empty_like(dscale), torch.empty_like(dbias), torch.zeros(1, device=dev)
 
         def run_pipe(k):
             main = torch.cuda.current_stream()
-            for p in pipes:
+            for p in two:
                 p["stream"].wait_stream(main)
             for i in range(k):
-                p = pipes[i % 2]
+                p = two[i % 2]
                 with torch.cuda.stream(p["stream"]):
                     p["step"].train_dev(sources_dev, vecs_dev, feat, scale, bias, p["dfeat"], p["dv"], p["ds"], p["db"], p["ls"])
-            for p in pipes:
+            for p in two:
                 main.wait_stream(p["stream"])
 
         run_pipe(max(args.warmup, 4))
@@ -530,7 +532,7 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
                               "drain included; this arm issues no collective); same kernels and bits as `value`; the gain is small because the STFT alone already runs "
                               "the part into its power cap and the synthesizer kernels lose throughput on fewer SMs "
                               "(tools/pipeline_probe.py, profiles/r2_pipeline_probe.json)")
-        for p in pipes:
+        for p in two:
             p["step"].plan.set_sm_budget(0)
 
     # primary: the host supplies the N source waveforms (fp32), the mixture (their sum, dataset/music.py:127) is formed
@@ -581,9 +583,9 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
     h2d_pcm = pcm_host.numel() * 2 + vecs_host.numel() * 4
     d2h = 4 + dvecs_host.numel() * 4
     e2e = dict(value=per(ms_e2e), unit=UNIT, h2d_bytes_per_step=h2d_src, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
-               pipeline_depth=2, timer="host wall clock around the K steps, synchronised on both sides",
+               pipeline_depth=TRAIN_DEPTH, timer="host wall clock around the K steps, synchronised on both sides",
                api="avsep_step_train_host_async (C-ABI): pinned host SOURCE waveforms [N,B,L] fp32 + K-vectors in, mixture summed "
-                   "on the GPU (avsep_step_set_mix_on_device), loss + dvecs out; 2 steps in flight on 2 streams"
+                   f"on the GPU (avsep_step_set_mix_on_device), loss + dvecs out; {TRAIN_DEPTH} steps in flight on {TRAIN_DEPTH} streams"
                    + ("; [loss, count] all-reduced (NCCL, async) every step" if world > 1 else ""),
                copy_roof=dict(ms_per_step=ms_copy_f32, gbytes_per_s_per_gpu=sources_host.numel() * 4 / (ms_copy_f32 * 1e-3) / 1e9,
                               frac=ms_copy_f32 / (ms_e2e / args.steps),
@@ -651,7 +653,8 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
                                "algorithmic fp32-equivalent FLOPs (0.536 GFLOP/signal)" if top["bound"] == "tensor" else
                                "algorithmic bytes per SURVEY.md section 8(d) (feat_sound counted once: fused fwd+bwd)")
     step.close()
-    step_b.close()
+    for s_ in more_steps:
+        s_.close()
     return dict(value=value, ms_total=ms_total, launches=int(launches), loss=loss_val, loss_global=loss_global, explicit=explicit,
                 pipelined=pipelined,
                 e2e=e2e, loss_e2e=dict(sources_only=loss_host, explicit_mixture=loss_host_full, pcm16=loss_host_pcm), clocks=clocks,
