@@ -274,11 +274,11 @@ def kernel_entry(name, N, B, ms, pk, share=None, executed=None, note=None):
         d = dict(kernel=name, ms=ms, share=share, bound="tensor", achieved=ach, peak=pk["tensor"], unit="TFLOP/s",
                  frac=ach / pk["tensor"], executed_over_algorithmic=ex, executed_tflops=ex * ach,
                  tensor_pipe_frac=ex * ach / pk["tensor"], frac_of_sustained_peak=ach / pk["tensor_sustained"],
-                 algorithmic_flops_per_launch=a["flops"] * B)
+                 frac_of_nominal_2250=ach / 2250.0, algorithmic_flops_per_launch=a["flops"] * B)
     else:
         ach = a["bytes"] * B / (ms * 1e-3) / 1e9
         d = dict(kernel=name, ms=ms, share=share, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
-                 algorithmic_bytes_per_launch=a["bytes"] * B)
+                 frac_of_nominal_8000=ach / 8000.0, algorithmic_bytes_per_launch=a["bytes"] * B)
     if note:
         d["note"] = note
     return d
@@ -286,7 +286,8 @@ def kernel_entry(name, N, B, ms, pk, share=None, executed=None, note=None):
 
 def roofline_of(top, ncu_name, pk, note):
     return dict(kernel=top["kernel"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"],
-                frac=top["frac"], traffic=ncu_traffic(ncu_name),
+                frac=top["frac"], frac_of_nominal=top.get("frac_of_nominal_8000", top.get("frac_of_nominal_2250")),
+                peak_nominal=(8000.0 if top["bound"] == "hbm" else 2250.0), traffic=ncu_traffic(ncu_name),
                 traffic_unit="bytes per launch (dram read + write), ncu --set full: profiles/r2_ncu_full_summary.txt (r1_... for "
                              "kernels unchanged since round 1)",
                 algorithmic_bytes_per_launch=top.get("algorithmic_bytes_per_launch"),

@@ -411,6 +411,20 @@ def test_sm_budget_does_not_change_results():
         plan.set_sm_budget(1)
 
 
+def test_separate_without_sources():
+    """Edge case of the staged operand kernel: N = 0 (mixture reconstruction only, (re, im) input) equals the (mag, phase) inverse."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    mix = (torch.rand((2, L), device="cuda", generator=g) - 0.5) * 0.9
+    mag, ph, re, im = av.stft(mix, complex_parts=True)
+    none = torch.empty((0, 2, 256, mag.shape[-1]), device="cuda")
+    a = av.separate(none, None, None, re_mix=re, im_mix=im)
+    b = av.istft(mag, ph)
+    _sync()
+    assert a.shape == (2, 1, 65280)
+    assert float((a[:, 0] - b).abs().max()) / float(b.abs().max()) < 2e-5
+    assert float((a[:, 0] - mix[:, :65280]).abs().max()) < 1e-4          # iSTFT(STFT(x)) = x
+
+
 def test_separate_with_complex_parts_equals_magphase():
     B, N = 1, 2
     src = O.synth_sources(B, N, seed=8)
