@@ -376,6 +376,29 @@ def test_eval_step_from_sources_alone(N, B):
     st.close()
 
 
+def test_prepare_inferdata_caches_per_audio_tensor():
+    """inference.py:537-569 calls prepare_inferdata once per video frame on the same audio: the drop-in answers repeat calls on the
+    same, unmodified tensor object from its cache (no launch), recomputes after an in-place change or for another tensor."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mag = torch.rand((1, 1, 512, 256), device="cuda", generator=g) + 0.01
+    ph = torch.zeros_like(mag)
+    av.clear_inferdata_cache()
+    _, w0, l0, _ = av.prepare_inferdata((mag, ph), None, None)
+    before = av.launch_count()
+    _, w1, l1, _ = av.prepare_inferdata((mag, ph), None, None)
+    assert av.launch_count() == before and w1 is w0 and l1 is l0
+    mag.mul_(2.0)                                                   # in-place change bumps the version counter: recompute
+    _, w2, l2, _ = av.prepare_inferdata((mag, ph), None, None)
+    assert av.launch_count() > before and w2 is not w0
+    torch.cuda.synchronize()
+    assert float((w2 - 2.0 * w0).abs().max()) / float(w2.abs().max()) < 1e-6
+    _, w3, _, _ = av.prepare_inferdata((mag.clone(), ph), None, None)     # another tensor object: recompute, same values
+    _, w4, _, _ = av.prepare_inferdata((mag, ph), None, None, cache=False)
+    torch.cuda.synchronize()
+    assert w3 is not w2 and torch.equal(w3, w2) and torch.equal(w4, w2)
+    av.clear_inferdata_cache()
+
+
 def test_long_clip_windows_vs_oracle():
     """Config C4 (small): a 3-window clip, fixed masks; every window equals the oracle's single-window path."""
     rng = np.random.default_rng(3)
