@@ -175,8 +175,10 @@ constexpr int SYN_FS_THREADS = 128;
 constexpr int SYN_FS_GROUPS = 4;                       // pixel groups of 128 x 4 px walked by one CTA
 constexpr int SYN_FS_SMEM = SYN_KCHUNK * SYN_FS_THREADS * 16;  // 64 KB staging
 
-template <int NS, bool FULLK>
-__global__ void __launch_bounds__(SYN_FS_THREADS, 3)
+// PIT = true: instead of the list-form loss, the per-sample NS x NS matrix  lm[i][j] = sum w * l(pred_j, target_i)  of the SoP++ audio-only
+// step (PitWrapper._opt_perm_loss, criterion.py:138-176) leaves the CTA as NS^2 doubles (reduced by pit_fwd_fin_kernel).
+template <int NS, bool FULLK, bool PIT>
+__global__ void __launch_bounds__(SYN_FS_THREADS, (PIT && NS > 2) ? 2 : 3)
 synth_fwd_staged_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
                         const float* __restrict__ bias, int B, int K, int HW, int act, float* __restrict__ out, int loss_kind,
                         const float* __restrict__ gt, const float* __restrict__ weight, double* __restrict__ partial) {
@@ -193,6 +195,11 @@ synth_fwd_staged_kernel(const float* __restrict__ feat, const float* __restrict_
   const float* fbase = feat + (size_t)b * K * HW;
   constexpr int HALF = SYN_KCHUNK / 2;
   float lsum = 0.f;
+  float lm[PIT ? NS : 1][PIT ? NS : 1];
+#pragma unroll
+  for (int i = 0; i < (PIT ? NS : 1); ++i)
+#pragma unroll
+    for (int j = 0; j < (PIT ? NS : 1); ++j) lm[i][j] = 0.f;
   auto issue = [&](int px, int k0) {                   // feat[k0 .. k0 + 16) of the thread's 4 pixels -> its column
 #pragma unroll
     for (int k = k0; k < k0 + HALF; ++k)
@@ -244,6 +251,7 @@ synth_fwd_staged_kernel(const float* __restrict__ feat, const float* __restrict_
     if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
     accumulate(HALF);
     if (more) issue(px_next, HALF);
+    float prs[PIT ? NS : 1][4];
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       const size_t o = ((size_t)n * B + b) * HW + px;
@@ -252,16 +260,35 @@ synth_fwd_staged_kernel(const float* __restrict__ feat, const float* __restrict_
       for (int e = 0; e < 4; ++e) {
         const float zz = z[n][e] + bz;
         pr[e] = act == AVSEP_ACT_SIGMOID ? __frcp_rn(1.0f + expf(-zz)) : zz;     // == 1 / (1 + exp(-z)), correctly rounded
+        if (PIT) prs[n][e] = pr[e];
       }
       *reinterpret_cast<float4*>(out + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);
-      if (loss_kind != AVSEP_LOSS_NONE) {
+      if (!PIT && loss_kind != AVSEP_LOSS_NONE) {
         const float tt[4] = {tgt[n].x, tgt[n].y, tgt[n].z, tgt[n].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) lsum += w[e] * loss_elem_fast(loss_kind, pr[e], tt[e]);
       }
     }
+    if (PIT) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const float tt[4] = {tgt[i].x, tgt[i].y, tgt[i].z, tgt[i].w};
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) lm[PIT ? i : 0][PIT ? j : 0] += w[e] * loss_elem_fast(loss_kind, prs[PIT ? j : 0][e], tt[e]);
+      }
+    }
   }
-  if (loss_kind != AVSEP_LOSS_NONE) {
+  if (PIT) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const double tot = block_sum<double>((double)lm[PIT ? i : 0][PIT ? j : 0], red);
+        if (tid == 0) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NS * NS) + i * NS + j] = tot;
+      }
+  } else if (loss_kind != AVSEP_LOSS_NONE) {
     const double tot = block_sum<double>((double)lsum, red);
     if (tid == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
   }
@@ -789,7 +816,7 @@ static int synth_forward_n(const float* feat, const float* vecs, const float* sc
   const int bx = staged ? ceil_div(HW, SYN_FS_THREADS * 4 * SYN_FS_GROUPS) : (vec4 ? lay.fwd_blocks_x : ceil_div(HW, SYN_FWD_THREADS));
   dim3 grid(bx, B);
   if (staged) {
-    auto kern = K == SYN_KCHUNK ? synth_fwd_staged_kernel<NS, true> : synth_fwd_staged_kernel<NS, false>;
+    auto kern = K == SYN_KCHUNK ? synth_fwd_staged_kernel<NS, true, false> : synth_fwd_staged_kernel<NS, false, false>;
     AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_FS_SMEM));
     kern<<<grid, SYN_FS_THREADS, SYN_FS_SMEM, stream>>>(feat, vecs, scale, bias, B, K, HW, act, out, loss_kind, gt, weight, partial);
   } else if (vec4)
@@ -1015,15 +1042,37 @@ int avsep_synth_forward_pit(const float* feat_dev, const float* vecs_dev, const 
   cudaStream_t stream = (cudaStream_t)stream_;
   const SynthScratch lay = synth_scratch_layout(B, N, K, HW);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(scratch_dev) + lay.loss_partial);
-  dim3 grid(lay.fwd_blocks_x, B);
-  switch (N) {
-    case 1: synth_fwd_pit_kernel<1><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
-    case 2: synth_fwd_pit_kernel<2><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
-    case 3: synth_fwd_pit_kernel<3><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
-    default: synth_fwd_pit_kernel<4><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+  const bool staged = K <= SYN_KCHUNK && (reinterpret_cast<uintptr_t>(feat_dev) & 15u) == 0;
+  const int bx = staged ? ceil_div(HW, SYN_FS_THREADS * 4 * SYN_FS_GROUPS) : lay.fwd_blocks_x;
+  dim3 grid(bx, B);
+  if (staged) {
+    // staged columns (cp.async, half-K pipelined) like the plain forward: 0.93-0.96 of the HBM roofline instead of 0.8
+    auto launch = [&](auto kern) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_FS_SMEM);
+      if (e != cudaSuccess) return e;
+      kern<<<grid, SYN_FS_THREADS, SYN_FS_SMEM, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind,
+                                                          gt_dev, weight_dev, partial);
+      return cudaSuccess;
+    };
+    const bool fullk = K == SYN_KCHUNK;
+    cudaError_t e;
+    switch (N) {
+      case 1: e = fullk ? launch(synth_fwd_staged_kernel<1, true, true>) : launch(synth_fwd_staged_kernel<1, false, true>); break;
+      case 2: e = fullk ? launch(synth_fwd_staged_kernel<2, true, true>) : launch(synth_fwd_staged_kernel<2, false, true>); break;
+      case 3: e = fullk ? launch(synth_fwd_staged_kernel<3, true, true>) : launch(synth_fwd_staged_kernel<3, false, true>); break;
+      default: e = fullk ? launch(synth_fwd_staged_kernel<4, true, true>) : launch(synth_fwd_staged_kernel<4, false, true>); break;
+    }
+    AVSEP_CUDA(e);
+  } else {
+    switch (N) {
+      case 1: synth_fwd_pit_kernel<1><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+      case 2: synth_fwd_pit_kernel<2><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+      case 3: synth_fwd_pit_kernel<3><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+      default: synth_fwd_pit_kernel<4><<<grid, SYN_FWD_THREADS, 0, stream>>>(feat_dev, vecs_dev, scale_dev, bias_dev, B, K, HW, activation, out_dev, loss_kind, gt_dev, weight_dev, partial); break;
+    }
   }
   AVSEP_LAUNCH_CHECK();
-  pit_fwd_fin_kernel<<<B, 32, 0, stream>>>(partial, lay.fwd_blocks_x, N * N, 1.0 / (double)HW, lossmat_dev);
+  pit_fwd_fin_kernel<<<B, 32, 0, stream>>>(partial, bx, N * N, 1.0 / (double)HW, lossmat_dev);
   AVSEP_LAUNCH_CHECK();
   return AVSEP_OK;
 }
