@@ -574,13 +574,15 @@ constexpr int SYN_TR_THREADS = 128;
 constexpr int SYN_TR_GROUPS = 4;                       // pixel groups of 128 x 4 px walked by one CTA
 constexpr int SYN_TR_SMEM = 32 * SYN_TR_THREADS * 16;  // 64 KB staging
 
-template <int NS, bool FULLK>
+// BWD = true: the stand-alone backward (plain autograd: InnerProd.forward + a criterion, PitWrapper) on the same staged columns:
+// no pass 1, dz from the SAVED masks with torch's two-step gradient (or given as dz_in), then pass 2 as in training.
+template <int NS, bool FULLK, bool BWD>
 __global__ void __launch_bounds__(SYN_TR_THREADS, (NS <= 2 ? 3 : 2))
 synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vecs, const float* __restrict__ scale,
                    const float* __restrict__ bias, int B, int K, int HW, int act, int loss_kind, const float* __restrict__ gt,
                    const float* __restrict__ weight, const float* __restrict__ gscale, float inv_count, float* __restrict__ pred,
                    double* __restrict__ loss_partial, float* __restrict__ dfeat, float* __restrict__ s_partial,
-                   float* __restrict__ dz_partial, int Kp) {
+                   float* __restrict__ dz_partial, int Kp, const float* __restrict__ dz_in) {
   extern __shared__ float4 stage[];                    // [32][SYN_TR_THREADS], column = thread (private)
   __shared__ float vs[NS][SYN_KCHUNK];
   __shared__ float red[SYN_TR_THREADS / 32][NS * SYN_KCHUNK + NS];
@@ -593,7 +595,7 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
   }
   __syncthreads();
   const float bz = bias ? bias[0] : 0.f;
-  const float g = (gscale ? gscale[0] : 1.f) * inv_count;
+  const float g = (BWD && dz_in) ? 1.f : (gscale ? gscale[0] : 1.f) * inv_count;
   const float* fbase = feat + (size_t)b * K * HW;
   float* dbase = dfeat + (size_t)b * K * HW;
   float S[NS][SYN_KCHUNK];
@@ -617,10 +619,35 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
     cp_async_commit();
     // small streams overlap the feat loads
     float w[4] = {1.f, 1.f, 1.f, 1.f};
-    if (weight) {
+    if (weight && !(BWD && dz_in)) {
       const float4 t4 = *reinterpret_cast<const float4*>(weight + (size_t)b * HW + px);
       w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
     }
+    float dz[NS][4];
+    if (BWD) {
+      // ---- dz from the saved masks: g * w * dl/dp * act'(p), torch's two-step form (synth_bwd_kernel computes the same), or given
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
+        const size_t o = ((size_t)n * B + b) * HW + px;
+        if (dz_in) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dz_in + o);
+          dz[n][0] = d4.x; dz[n][1] = d4.y; dz[n][2] = d4.z; dz[n][3] = d4.w;
+        } else {
+          const float4 p4 = *reinterpret_cast<const float4*>(pred + o);
+          const float4 t4 = *reinterpret_cast<const float4*>(gt + o);
+          const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float d = g * w[e] * loss_grad(loss_kind, pp[e], tt[e]);
+            if (act == AVSEP_ACT_SIGMOID) d *= (1.f - pp[e]) * pp[e];
+            dz[n][e] = d;
+          }
+        }
+        dzs[n] += (dz[n][0] + dz[n][1]) + (dz[n][2] + dz[n][3]);
+      }
+      cp_async_wait_all();
+    } else {
     float4 tgt[NS];
 #pragma unroll
     for (int n = 0; n < NS; ++n) tgt[n] = *reinterpret_cast<const float4*>(gt + ((size_t)n * B + b) * HW + px);
@@ -646,7 +673,6 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
       }
     }
     // ---- activation, loss, dz --------------------------------------------------------------------------------
-    float dz[NS][4];
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       const size_t o = ((size_t)n * B + b) * HW + px;
@@ -661,6 +687,7 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
       }
       *reinterpret_cast<float4*>(pred + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);
       dzs[n] += (dz[n][0] + dz[n][1]) + (dz[n][2] + dz[n][3]);
+    }
     }
     // ---- pass 2: dfeat out, S accumulation from the parked feat ------------------------------------------------
 #pragma unroll
@@ -699,7 +726,7 @@ synth_train_kernel(const float* __restrict__ feat, const float* __restrict__ vec
   }
   const double ltot = block_sum<double>((double)lsum, lred);      // contains the __syncthreads that publishes red[][]
   const size_t cta = (size_t)b * gridDim.x + blockIdx.x;
-  if (tid == 0) loss_partial[cta] = ltot;
+  if (tid == 0 && !BWD) loss_partial[cta] = ltot;
   for (int i = tid; i < NS * SYN_KCHUNK + NS; i += blockDim.x) {
     float r = 0.f;
 #pragma unroll
@@ -846,7 +873,17 @@ static int synth_backward_n(const float* feat, const float* vecs, const float* s
   float* tvec = reinterpret_cast<float*>(sc + lay.tvec);
   dim3 grid(lay.bwd_chunks, B, lay.Kp / SYN_KCHUNK);
   const float inv_count = (float)(1.0 / ((double)B * (double)HW * (double)NS));
-  if (dz)
+  // the staged kernel (thread-private cp.async columns of synth_train_kernel, pass 2 only) when it applies: K <= 32, dfeat
+  // wanted, 16-byte rows; its partial sums have the layout the reduce / final kernels below read (same 2048 px per CTA)
+  const bool staged = dfeat != nullptr && K <= SYN_KCHUNK && (HW % 4) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dfeat) & 15u) == 0;
+  if (staged) {
+    auto kern = (K == SYN_KCHUNK) ? synth_train_kernel<NS, true, true> : synth_train_kernel<NS, false, true>;
+    AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_TR_SMEM));
+    dim3 sgrid(lay.bwd_chunks, B);
+    kern<<<sgrid, SYN_TR_THREADS, SYN_TR_SMEM, stream>>>(feat, vecs, scale, nullptr, B, K, HW, act, loss_kind, gt, weight, gscale, inv_count,
+                                                         const_cast<float*>(pred), nullptr, dfeat, s_partial, dz_partial, lay.Kp, dz);
+  } else if (dz)
     synth_bwd_kernel<NS, true><<<grid, SYN_BWD_THREADS, 0, stream>>>(feat, vecs, scale, B, K, HW, act, loss_kind, pred, gt,
                                                                      weight, gscale, dz, inv_count, dfeat, s_partial,
                                                                      dz_partial, lay.Kp);
@@ -879,12 +916,12 @@ static int synth_train_n(const float* feat, const float* vecs, const float* scal
   float* dz_partial = reinterpret_cast<float*>(sc + lay.dz_partial);
   const int chunks = ceil_div(HW, SYN_TR_THREADS * 4 * SYN_TR_GROUPS);      // == lay.bwd_chunks (same 2048 px per CTA)
   static_assert(SYN_TR_THREADS * SYN_TR_GROUPS == SYN_BWD_THREADS * SYN_BWD_ITERS, "scratch layout shared with the backward kernel");
-  auto kern = (K == SYN_KCHUNK) ? synth_train_kernel<NS, true> : synth_train_kernel<NS, false>;
+  auto kern = (K == SYN_KCHUNK) ? synth_train_kernel<NS, true, false> : synth_train_kernel<NS, false, false>;
   AVSEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_TR_SMEM));
   dim3 grid(chunks, B);
   const float inv_count = (float)(1.0 / ((double)B * (double)HW * (double)NS));
   kern<<<grid, SYN_TR_THREADS, SYN_TR_SMEM, stream>>>(feat, vecs, scale, bias, B, K, HW, act, loss_kind, gt, weight, gscale, inv_count,
-                                                       pred, loss_partial, dfeat, s_partial, dz_partial, lay.Kp);
+                                                       pred, loss_partial, dfeat, s_partial, dz_partial, lay.Kp, nullptr);
   AVSEP_LAUNCH_CHECK();
   synth_finalize_kernel<<<K + 2, 256, 0, stream>>>(s_partial, dz_partial, loss_partial, vecs, scale, B, NS, K, lay.Kp, chunks,
                                                     chunks * B, 1.0 / ((double)B * (double)HW * (double)NS), dvecs, dscale, dbias, loss);
