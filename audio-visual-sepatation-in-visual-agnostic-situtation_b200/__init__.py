@@ -17,7 +17,7 @@ from .ops import (Plan, clear_plans, device_check, get_plan, istft, launch_count
 from . import modules
 from .modules import BCELoss, BaseLoss, Bias, InnerProd, L1Loss, L2Loss, PitWrapper, activate
 from . import hotpath
-from .hotpath import (Step, _mix_n_and_stft, _stft, assemble_windows, calc_metrics, clip_windows, get_spec, istft_reconstruction, prepare,
+from .hotpath import (Step, StepPipeline, _mix_n_and_stft, _stft, assemble_windows, calc_metrics, clip_windows, get_spec, istft_reconstruction, prepare,
                       clear_inferdata_cache, prepare_inferdata, recover_aud, recover_aud_arrays,
                       separate_long_clip, stft_batch, warp, warpgrid)
 from . import parallel
@@ -25,7 +25,7 @@ from . import bss_metrics
 from .bss_metrics import bss_eval_batch, bss_eval_batch_torch
 
 __all__ = [
-    "AvsepError", "LIB_PATH", "clear_inferdata_cache", "ops", "modules", "hotpath", "parallel", "bss_metrics", "bss_eval_batch", "bss_eval_batch_torch",
+    "AvsepError", "LIB_PATH", "StepPipeline", "clear_inferdata_cache", "ops", "modules", "hotpath", "parallel", "bss_metrics", "bss_eval_batch", "bss_eval_batch_torch",
     "Plan", "get_plan", "clear_plans", "device_check", "launch_count",
     "stft", "stft_mix", "istft", "pcm16_to_wave", "separate", "warp", "warpgrid", "prepare", "calc_metrics", "istft_reconstruction",
     "_stft", "_mix_n_and_stft", "stft_batch", "get_spec", "prepare_inferdata", "recover_aud", "recover_aud_arrays", "Step", "clip_windows", "assemble_windows", "separate_long_clip",

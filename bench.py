@@ -502,22 +502,17 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
     # reported beside `value`, which stays the one-step-at-a-time number.
     pipelined = None
     if src_only:
-        two = pipes[:2]
-        for p in two:
-            p["step"].set_mix_on_device(True)
-            p["step"].plan.set_sm_budget(PIPE_SM_BUDGET)
-            p["dv"], p["ds"], p["db"], p["ls"] = torch.empty_like(dvecs), torch.empty_like(dscale), torch.empty_like(dbias), torch.zeros(1, device=dev)
+        pipe = av.StepPipeline(B, N, K, L, depth=2, stft_sm_budget=PIPE_SM_BUDGET, graph=not args.no_graph)
+        outs = [dict(dfeat=pipes[i]["dfeat"], dv=torch.empty_like(dvecs), ds=torch.empty_like(dscale), db=torch.empty_like(dbias),
+                     ls=torch.zeros(1, device=dev)) for i in range(2)]
 
         def run_pipe(k):
-            main = torch.cuda.current_stream()
-            for p in two:
-                p["stream"].wait_stream(main)
-            for i in range(k):
-                p = two[i % 2]
-                with torch.cuda.stream(p["stream"]):
-                    p["step"].train_dev(sources_dev, vecs_dev, feat, scale, bias, p["dfeat"], p["dv"], p["ds"], p["db"], p["ls"])
-            for p in two:
-                main.wait_stream(p["stream"])
+            for _ in range(k):
+                slot = pipe.next()
+                o = outs[slot.index]
+                with torch.cuda.stream(slot.stream):
+                    slot.step.train_dev(sources_dev, vecs_dev, feat, scale, bias, o["dfeat"], o["dv"], o["ds"], o["db"], o["ls"])
+            pipe.synchronize()
 
         run_pipe(max(args.warmup, 4))
         barrier()
@@ -528,13 +523,13 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
         barrier()
         ms_p = parallel.max_over_ranks(y0.elapsed_time(y1), device=dev)
         pipelined = dict(value=B * world * args.steps / (ms_p * 1e-3), unit=UNIT, ms_per_step=ms_p / args.steps,
-                         loss=[float(pipes[0]["ls"]), float(pipes[1]["ls"])], steps_in_flight=2, stft_sm_budget=PIPE_SM_BUDGET,
+                         loss=[float(outs[0]["ls"]), float(outs[1]["ls"])], steps_in_flight=2, stft_sm_budget=PIPE_SM_BUDGET,
+                         api="avsep_b200.StepPipeline (two Step objects on two streams, round-robin)",
                          note="two steps in flight on two streams, inputs resident in HBM, whole loop timed with CUDA events (fill and "
-                              "drain included; this arm issues no collective); same kernels and bits as `value`; the gain is small because the STFT alone already runs "
-                              "the part into its power cap and the synthesizer kernels lose throughput on fewer SMs "
-                              "(tools/pipeline_probe.py, profiles/r2_pipeline_probe.json)")
-        for p in two:
-            p["step"].plan.set_sm_budget(0)
+                              "drain included; this arm issues no collective); same kernels and bits as `value`; the gain is small because "
+                              "the STFT alone already runs the part into its power cap and the synthesizer kernels lose throughput on "
+                              "fewer SMs (tools/pipeline_probe.py, profiles/r2_pipeline_probe.json)")
+        pipe.close()
 
     # primary: the host supplies the N source waveforms (fp32), the mixture (their sum, dataset/music.py:127) is formed
     # on the GPU; secondary: the host also supplies the mixture waveform; opt-in: the sources as 16-bit PCM

@@ -399,6 +399,33 @@ def test_prepare_inferdata_caches_per_audio_tensor():
     av.clear_inferdata_cache()
 
 
+def test_step_pipeline_equals_serial_steps():
+    """StepPipeline (two steps in flight, STFT capped at 80 SMs): every step's results are bit-identical to a lone Step's."""
+    B, N, K = 3, 2, 32
+    waves, feat, vecs, scale, bias = _inputs(B, N, K, seed=77)
+    c = lambda a: torch.from_numpy(a).cuda()
+    src, tv, tf, tsc, tb = c(np.ascontiguousarray(waves[1:])), c(vecs), c(feat), c(scale), c(bias)
+    st = av.Step(B, N, K, L)
+    st.set_mix_on_device(True)
+    dfeat0, loss0 = torch.empty_like(tf), torch.empty(1, device="cuda")
+    st.train_dev(src, tv, tf, tsc, tb, dfeat0, None, None, None, loss0)
+    torch.cuda.synchronize()
+    pipe = av.StepPipeline(B, N, K, L, depth=2)
+    dfe = [torch.empty_like(tf) for _ in range(2)]
+    los = [torch.empty(1, device="cuda") for _ in range(2)]
+    for _ in range(6):                                               # direct, capture and replay calls of both slots
+        slot = pipe.next()
+        with torch.cuda.stream(slot.stream):
+            dfe[slot.index].zero_()
+            slot.step.train_dev(src, tv, tf, tsc, tb, dfe[slot.index], None, None, None, los[slot.index])
+    pipe.synchronize()
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert float(los[i]) == float(loss0) and torch.equal(dfe[i], dfeat0)
+    pipe.close()
+    st.close()
+
+
 def test_long_clip_windows_vs_oracle():
     """Config C4 (small): a 3-window clip, fixed masks; every window equals the oracle's single-window path."""
     rng = np.random.default_rng(3)
