@@ -466,6 +466,9 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
     def run_e2e(k, mode):
         for p in pipes:
             p["step"].set_mix_on_device(mode != "full")
+            # the PCM16 arm is compute-bound (0.39 ms of copy per step), so the kernels of the steps in flight overlap: cap the
+            # persistent STFT grid as StepPipeline does, otherwise two all-SM STFTs and a synthesizer kernel interleave at random
+            p["step"].plan.set_sm_budget(PIPE_SM_BUDGET if mode == "pcm16" else 0)
         for i in range(k):
             p = pipes[i % TRAIN_DEPTH]
             p["stream"].synchronize()                              # step i - TRAIN_DEPTH done: its loss is on the host now
@@ -557,6 +560,7 @@ def train_section(av, parallel, dist, args, rank, world, local, dev, pk, sampler
 
     for p in pipes:
         p["step"].set_mix_on_device(False)
+        p["step"].plan.set_sm_budget(0)
     step.set_mix_on_device(src_only)                 # pipes[0] is the value arm's Step: back to the input layout step_dev() passes
     # same inputs, same kernels through the host-buffer entry point: the losses must agree (a gross mismatch = a bug;
     # the exact values are reported in the JSON line)
