@@ -132,7 +132,7 @@ ref = (loss.clone(), dfeat.clone(), pred.clone())
 # same two-stream dependent pipeline WITHOUT partitioning (ordinary streams, all SMs): what the block scheduler does on its own
 s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
 out["pipelined_unpartitioned"] = pipelined(s_a, s_b)
-for budget in (48, 64, 80):
+for budget in [int(x) for x in os.environ.get("PROBE_BUDGETS", "48,64,80").split(",")]:
     plan.set_sm_budget(budget)
     out[f"pipelined_unpartitioned_k1_budget_{budget}"] = pipelined(s_a, s_b)
 for front_sms in [int(x) for x in os.environ.get("PROBE_SPLITS", "40,48,56,64,72").split(",")]:
