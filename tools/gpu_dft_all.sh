@@ -1,5 +1,5 @@
 #!/bin/bash
-# one-GPU check after a transform-kernel change: all GPU parity tests, then the bench
+# one-GPU check after a kernel change: all GPU parity tests, then the bench with its per-kernel summary
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/t_all.log
