@@ -165,6 +165,32 @@ def test_istft_matches_torch_istft(golden):
     assert np.max(np.abs(rt - mix[:65280])) < 2e-6        # round trip (SURVEY.md 8(a) row 9 probe)
 
 
+def test_stft_and_istft_match_scipy_signal():
+    """Second independent implementation beside torch.stft / torch.istft: scipy.signal.stft / istft with librosa's conventions
+    (librosa itself takes its window from scipy.signal.get_window): periodic Hann of 1022, hop 256, reflect ('even') centre
+    padding, no scaling.  librosa is not installable here, so the oracle's STFT / iSTFT restatement (dataset/base.py:142-147,
+    utils.py:101-104) is pinned by two unrelated code bases instead."""
+    import scipy.signal
+    rng = np.random.default_rng(11)
+    win_sum = O.hann_periodic(1022).sum()
+    for length in (65535, 40000, 3000):
+        x = (rng.standard_normal(length) * 0.3).astype(np.float32)
+        spec = O.stft_complex(x)
+        _, _, z = scipy.signal.stft(x.astype(np.float64), window="hann", nperseg=1022, noverlap=1022 - 256, nfft=1022, detrend=False,
+                                    return_onesided=True, boundary="even", padded=False, scaling="spectrum")
+        z = z * win_sum                                              # scipy divides by sum(window), librosa does not scale
+        assert z.shape == spec.shape == (512, 1 + length // 256)
+        assert np.max(np.abs(z - spec)) / np.max(np.abs(spec)) < 1e-12
+        # inverse: librosa.istft(spec, hop_length=256) -> hop * (T - 1) samples, window-sum-square normalised, centre trimmed
+        rec = O.istft(spec)
+        _, y = scipy.signal.istft(spec / win_sum, window="hann", nperseg=1022, noverlap=1022 - 256, nfft=1022, input_onesided=True,
+                                  boundary=True, scaling="spectrum")
+        n = min(rec.shape[0], y.shape[0])
+        assert rec.shape[0] == 256 * (spec.shape[1] - 1) and abs(rec.shape[0] - y.shape[0]) <= 1022
+        assert np.max(np.abs(rec[:n] - y[:n])) < 1e-10
+        assert np.max(np.abs(rec[:n] - x[:n])) < 1e-6               # both reconstruct the input
+
+
 def test_calc_metrics_flow_matches_reference(golden):
     from oracle import bss_eval as BSS
     g = golden("calc_metrics")
