@@ -4,7 +4,6 @@ cuobjdump -sass libavsep_b200.so.  usage: sass_mnemonics.py > profiles/r2_sass_m
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "audio-visual-sepatation-in-visual-agnostic-situtation_b200", "libavsep_b200.so")
