@@ -1,4 +1,5 @@
-"""Time the fused SoP++ audio-only forward (masks + per-sample N x N PIT loss matrix in one pass over feat_sound) at the C2 shape."""
+"""Time the fused SoP++ audio-only forward (masks + per-sample N x N PIT loss matrix in one pass over feat_sound) and the
+stand-alone synthesizer backward (what PitWrapper / plain autograd run after it) at the C2 shape."""
 import os
 import sys
 
@@ -21,3 +22,11 @@ f=lambda: chk(lib.avsep_synth_forward_pit(feat.data_ptr(),vecs.data_ptr(),scale.
 ms=bench.time_calls(f,10)
 nbytes=B*(32*65536*4+N*65536*4+(N+1)*65536*4)
 print('forward_pit ms',ms,'GB/s',nbytes/ms/1e6)
+one = torch.ones(1, device='cuda')
+dfeat = torch.empty_like(feat); dvecs = torch.empty_like(vecs); dscale = torch.empty(K, device='cuda'); dbias = torch.empty(1, device='cuda')
+b = lambda: chk(lib.avsep_synth_backward(feat.data_ptr(), vecs.data_ptr(), scale.data_ptr(), B, N, K, 65536, 1, 3, out.data_ptr(), gt.data_ptr(),
+                                         w.data_ptr(), one.data_ptr(), None, dfeat.data_ptr(), dvecs.data_ptr(), dscale.data_ptr(), dbias.data_ptr(),
+                                         scratch.data_ptr(), st))
+ms = bench.time_calls(b, 10)
+nbytes = B * (32 * 65536 * 4 * 2 + (2 * N + 1) * 65536 * 4)
+print('backward ms', ms, 'GB/s', nbytes / ms / 1e6)
